@@ -1,0 +1,153 @@
+"""ctypes binding of the C-ABI shared library (``include/b200q.h``) and its in-tree build.
+
+The library is built with plain ``nvcc`` for sm_100a (no torch headers) into
+``convnet_quantization_b200/libb200q.so``; there is deliberately NO CPU fallback:
+if the library is missing, or no CUDA device is present, product calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+LIB_PATH = PKG_DIR / "libb200q.so"
+BUILD_DIR = PKG_DIR / "build"
+SOURCES = ("runtime.cu", "elementwise.cu", "simt.cu", "igemm_tc.cu", "net.cu")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC"]
+
+EXPORTS = (
+    "b200q_last_error", "b200q_abi_version", "b200q_quantize_nchw_to_nhwc", "b200q_quantize_flat",
+    "b200q_dequantize", "b200q_relu_q", "b200q_max_pool2x2_nhwc", "b200q_minmax", "b200q_conv3x3_first",
+    "b200q_quantize_conv3x3_first", "b200q_conv3x3_tc", "b200q_conv3x3_simt", "b200q_linear_tc",
+    "b200q_linear_simt", "b200q_linear_dequant", "b200q_linear_dynamic", "b200q_static_workspace_bytes",
+    "b200q_static_forward",
+)
+
+
+class B200QError(RuntimeError):
+    pass
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.sep not in cand or os.path.exists(cand)):
+            return cand
+    raise B200QError("nvcc not found")
+
+
+def _stale() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    t = LIB_PATH.stat().st_mtime
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "b200q.h"]
+    return any(p.stat().st_mtime > t for p in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every CUDA source for sm_100a and link ``libb200q.so`` in-tree."""
+    if not force and not _stale():
+        return LIB_PATH
+    BUILD_DIR.mkdir(exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(src: str) -> Path:
+        obj = BUILD_DIR / (src[:-3] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise B200QError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose and r.stderr.strip():
+            print(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    tmp = LIB_PATH.with_suffix(".so.tmp")
+    cmd = [nvcc, "-shared", "-o", str(tmp), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a",
+           "-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise B200QError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+# ------------------------------------------------------------------ C structs (mirror include/b200q.h)
+class Requant(C.Structure):
+    _fields_ = [("mult", C.c_void_p), ("bdiv", C.c_void_p), ("zp_out", C.c_int32), ("relu", C.c_int32)]
+
+
+class Conv3x3(C.Structure):
+    _fields_ = [("cin", C.c_int32), ("cout", C.c_int32), ("img", C.c_int32), ("zp_x", C.c_int32),
+                ("w", C.c_void_p), ("corr", C.c_void_p), ("rq", Requant)]
+
+
+class Linear(C.Structure):
+    _fields_ = [("k", C.c_int32), ("n", C.c_int32), ("zp_x", C.c_int32),
+                ("w", C.c_void_p), ("corr", C.c_void_p), ("rq", Requant)]
+
+
+class StaticNet(C.Structure):
+    _fields_ = [("in_inv_scale", C.c_float), ("in_zp", C.c_int32), ("conv", Conv3x3 * 6),
+                ("fc1", Linear), ("fc2", Linear), ("out_scale", C.c_float)]
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_SIGNATURES = {
+    "b200q_quantize_nchw_to_nhwc": [_P, _P, _L, _I, _I, _I, _I, _F, _I, _P],
+    "b200q_quantize_flat": [_P, _P, _L, _F, _I, _P],
+    "b200q_dequantize": [_P, _P, _L, _F, _I, _P],
+    "b200q_relu_q": [_P, _P, _L, _I, _P],
+    "b200q_max_pool2x2_nhwc": [_P, _P, _L, _I, _I, _I, _P],
+    "b200q_minmax": [_P, _L, _P, _P, _P],
+    "b200q_conv3x3_first": [_P, _P, _L, C.POINTER(Conv3x3), _P],
+    "b200q_quantize_conv3x3_first": [_P, _P, _L, _F, C.POINTER(Conv3x3), _P],
+    "b200q_conv3x3_tc": [_P, _P, _L, C.POINTER(Conv3x3), _I, _P],
+    "b200q_conv3x3_simt": [_P, _P, _L, C.POINTER(Conv3x3), _P],
+    "b200q_linear_tc": [_P, _P, _L, C.POINTER(Linear), _P],
+    "b200q_linear_simt": [_P, _P, _L, C.POINTER(Linear), _P],
+    "b200q_linear_dequant": [_P, _P, _L, C.POINTER(Linear), _F, _P],
+    "b200q_linear_dynamic": [_P, _P, _L, _I, _I, _P, _P, _F, _P, _I, _P, _P, _P],
+    "b200q_static_forward": [C.POINTER(StaticNet), _P, _P, _L, _P, _L, C.POINTER(C.c_void_p), _P],
+}
+
+_lib = None
+
+
+def load(build_if_missing: bool = False) -> C.CDLL:
+    """dlopen ``libb200q.so`` and attach signatures.  Raises ``B200QError`` if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing and _stale():
+        build()
+    if not LIB_PATH.exists():
+        raise B200QError(f"{LIB_PATH} is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(there is no CPU fallback for the CUDA path)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise B200QError(f"{LIB_PATH} does not export {name}")
+    lib.b200q_last_error.restype = C.c_char_p
+    lib.b200q_last_error.argtypes = []
+    lib.b200q_abi_version.restype = C.c_int
+    lib.b200q_static_workspace_bytes.restype = C.c_int64
+    lib.b200q_static_workspace_bytes.argtypes = [C.c_int64]
+    for name, args in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    """Turn a negative status into a Python exception (the reference's error convention is exceptions only)."""
+    if rc != 0:
+        msg = load().b200q_last_error().decode(errors="replace")
+        raise B200QError(f"{what or 'b200q call'} failed with status {rc}: {msg}")

@@ -1,0 +1,62 @@
+// Whole static-PTQ SimpleConvNet forward: the call order of models/baseline_model.py:58-83 on the converted
+// (int8) model, as one C-ABI call that enqueues every kernel on the caller's stream.  No allocation, no sync.
+#include "common.cuh"
+
+using namespace b200q;
+
+namespace {
+constexpr int64_t BYTES_PER_IMG = 65536;  // largest activation: conv1/conv2 output, 32*32*64 uint8
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+int copy_tap(uint8_t* const* taps, int idx, const void* src, int64_t bytes, cudaStream_t s) {
+  if (taps == nullptr || taps[idx] == nullptr) return 0;
+  return check_cuda(cudaMemcpyAsync(taps[idx], src, (size_t)bytes, cudaMemcpyDeviceToDevice, s), "tap copy");
+}
+}  // namespace
+
+extern "C" int64_t b200q_static_workspace_bytes(int64_t b) {
+  if (b < 0) return B200Q_ERR_INVALID_ARG;
+  return 2 * align_up(b * BYTES_PER_IMG, 1024) + 1024;
+}
+
+extern "C" int b200q_static_forward(const b200q_static_net* net, const float* x, float* logits, int64_t b,
+                                    void* workspace, int64_t workspace_bytes, uint8_t* const* taps, void* stream) {
+  B200Q_REQUIRE(net && ((x && logits && workspace) || b == 0), "static_forward: null pointer");
+  B200Q_REQUIRE(b >= 0, "static_forward: negative batch");
+  if (b == 0) return 0;
+  B200Q_REQUIRE(workspace_bytes >= b200q_static_workspace_bytes(b), "static_forward: workspace too small (%lld < %lld)",
+                (long long)workspace_bytes, (long long)b200q_static_workspace_bytes(b));
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* A = reinterpret_cast<uint8_t*>(align_up((int64_t)(uintptr_t)workspace, 1024));
+  uint8_t* B = A + align_up(b * BYTES_PER_IMG, 1024);
+  int rc;
+#define STEP(call) do { rc = (call); if (rc) return rc; } while (0)
+
+  if (taps && taps[0])  // QuantStub output is only materialised when a parity test asks for it
+    STEP(b200q_quantize_nchw_to_nhwc(x, taps[0], b, 3, 32, 32, 4, net->in_inv_scale, net->in_zp, stream));
+  STEP(b200q_quantize_conv3x3_first(x, A, b, net->in_inv_scale, &net->conv[0], stream));
+  STEP(copy_tap(taps, 1, A, b * 65536, s));
+  STEP(b200q_conv3x3_tc(A, B, b, &net->conv[1], 0, stream));
+  STEP(copy_tap(taps, 2, B, b * 65536, s));
+  STEP(b200q_max_pool2x2_nhwc(B, A, b, 32, 32, 64, stream));
+  STEP(copy_tap(taps, 3, A, b * 16384, s));
+  STEP(b200q_conv3x3_tc(A, B, b, &net->conv[2], 0, stream));
+  STEP(copy_tap(taps, 4, B, b * 32768, s));
+  STEP(b200q_conv3x3_tc(B, A, b, &net->conv[3], 0, stream));
+  STEP(copy_tap(taps, 5, A, b * 32768, s));
+  STEP(b200q_max_pool2x2_nhwc(A, B, b, 16, 16, 128, stream));
+  STEP(copy_tap(taps, 6, B, b * 8192, s));
+  STEP(b200q_conv3x3_tc(B, A, b, &net->conv[4], 0, stream));
+  STEP(copy_tap(taps, 7, A, b * 16384, s));
+  STEP(b200q_conv3x3_tc(A, B, b, &net->conv[5], 0, stream));
+  STEP(copy_tap(taps, 8, B, b * 16384, s));
+  STEP(b200q_max_pool2x2_nhwc(B, A, b, 8, 8, 256, stream));
+  STEP(copy_tap(taps, 9, A, b * 4096, s));
+  STEP(b200q_linear_tc(A, B, b, &net->fc1, stream));
+  STEP(copy_tap(taps, 10, B, b * 512, s));
+  if (taps && taps[11]) STEP(b200q_linear_simt(B, taps[11], b, &net->fc2, stream));
+  STEP(b200q_linear_dequant(B, logits, b, &net->fc2, net->out_scale, stream));
+#undef STEP
+  return 0;
+}

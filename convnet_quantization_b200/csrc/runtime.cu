@@ -1,0 +1,88 @@
+// Host-side plumbing shared by every b200q entry point: error text, device checks, TMA descriptor encoding.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace b200q {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error("CUDA error %s (%s) at %s", cudaGetErrorName(e), cudaGetErrorString(e), what);
+  return B200Q_ERR_CUDA;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) {
+    set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// dims[0] is the contiguous dimension; strides_bytes[i] is the stride of dims[i+1] (rank-1 entries).
+// Element type is always uint8 here; OOB elements read as 0.
+int encode_tensor_map(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return B200Q_ERR_DRIVER;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void*>(gptr), gdim, gstr, bx, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dim0 %llu, box0 %u, swizzle %d)", (int)r, rank,
+              (unsigned long long)dims[0], box[0], swizzle_bytes);
+    return B200Q_ERR_DRIVER;
+  }
+  return 0;
+}
+
+}  // namespace b200q
+
+extern "C" const char* b200q_last_error(void) { return b200q::g_err; }
+extern "C" int b200q_abi_version(void) { return 1; }

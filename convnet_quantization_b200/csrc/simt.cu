@@ -1,0 +1,334 @@
+// CUDA-core (dp4a) kernels: the first convolution (cin=3, K=27: memory-bound, not tensor-core shaped),
+// small/dynamic linears, and a plain direct convolution used as a bring-up cross-check for the tcgen05 path.
+#include "common.cuh"
+
+namespace b200q {
+
+int launch_minmax(const float* x, int64_t n, float* out5, void* scratch, cudaStream_t s);
+int launch_quantize_flat(const float* x, uint8_t* y, int64_t n, float inv_scale, int zp, const float* qp_dev,
+                         cudaStream_t s);
+
+__device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+  return d;
+}
+
+// =========================================================================================================
+// First conv (cin = 3 stored as 4, cout = 64, 32x32 images), optionally fused with aten::quantize_per_tensor.
+// Block = 8 output rows x 32 columns of one image (256 threads, one pixel each, all 64 output channels).
+// The quantized halo (10 x 34 pixels, one 32-bit word per pixel) lives in shared memory; out-of-image taps hold
+// zp_x (real-domain zero), so acc_true = sum_all x*w - zp_x*sum_all w = raw - corr[interior][c] for every pixel.
+// Weights [9 taps][64 cout] words are read as broadcast uint4 (4 output channels per LDS.128).
+constexpr int C1_ROWS = 8;
+constexpr int C1_COUT = 64;
+
+template <bool FUSED_QUANT>
+__global__ void __launch_bounds__(256) conv1_kernel(const void* __restrict__ xin, uint8_t* __restrict__ y,
+                                                    const uint32_t* __restrict__ w_words,  // [64][9] words
+                                                    const int32_t* __restrict__ corr,      // [9][64], row 4 = interior
+                                                    const float* __restrict__ mult, const float* __restrict__ bdiv,
+                                                    int zp_x, int zp_out, int relu, float inv_scale, int img) {
+  __shared__ uint32_t s_in[(C1_ROWS + 2) * 34];
+  __shared__ uint4 s_w[9 * (C1_COUT / 4)];
+  __shared__ float s_mult[C1_COUT], s_bdiv[C1_COUT];
+  __shared__ int s_corr[C1_COUT];
+
+  const int tiles_per_img = img / C1_ROWS;
+  const int64_t image = blockIdx.x / tiles_per_img;
+  const int row0 = (blockIdx.x % tiles_per_img) * C1_ROWS;
+  const int tid = threadIdx.x;
+  const uint32_t zp_word = (uint32_t)zp_x * 0x01010101u;
+
+  for (int i = tid; i < 9 * C1_COUT; i += 256) {
+    // s_w[tap][c/4].{x,y,z,w} = word(tap, c)
+    const int tap = i / C1_COUT, c = i % C1_COUT;
+    reinterpret_cast<uint32_t*>(s_w)[tap * C1_COUT + c] = __ldg(w_words + c * 9 + tap);
+  }
+  if (tid < C1_COUT) {
+    s_mult[tid] = __ldg(mult + tid);
+    s_bdiv[tid] = __ldg(bdiv + tid);
+    s_corr[tid] = __ldg(corr + 4 * C1_COUT + tid);
+  }
+  for (int i = tid; i < (C1_ROWS + 2) * 34; i += 256) {
+    const int r = i / 34 + row0 - 1, c = i % 34 - 1;
+    uint32_t word = zp_word;
+    if (r >= 0 && r < img && c >= 0 && c < img) {
+      if constexpr (FUSED_QUANT) {
+        const float* x = reinterpret_cast<const float*>(xin) + image * 3 * img * img + r * img + c;
+        const uint32_t q0 = quantize_u8(__ldg(x), inv_scale, zp_x);
+        const uint32_t q1 = quantize_u8(__ldg(x + img * img), inv_scale, zp_x);
+        const uint32_t q2 = quantize_u8(__ldg(x + 2 * img * img), inv_scale, zp_x);
+        word = q0 | (q1 << 8) | (q2 << 16) | ((uint32_t)zp_x << 24);
+      } else {
+        word = __ldg(reinterpret_cast<const uint32_t*>(xin) + (image * img + r) * img + c);
+      }
+    }
+    s_in[i] = word;
+  }
+  __syncthreads();
+
+  const int lr = tid / 32, lc = tid % 32;
+  if (lc >= img) return;  // (img is 32 for this network; kept for smaller test geometries)
+  uint32_t xin9[9];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) xin9[kh * 3 + kw] = s_in[(lr + kh) * 34 + lc + kw];
+
+  const int lo = relu ? zp_out : 0;
+  uint8_t* out = y + ((image * img + row0 + lr) * img + lc) * (int64_t)C1_COUT;
+#pragma unroll
+  for (int cg = 0; cg < C1_COUT / 16; ++cg) {
+    uint32_t packed[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const uint4 wv = s_w[tap * (C1_COUT / 4) + cg * 4 + q];
+        a0 = dp4a_us(xin9[tap], wv.x, a0);
+        a1 = dp4a_us(xin9[tap], wv.y, a1);
+        a2 = dp4a_us(xin9[tap], wv.z, a2);
+        a3 = dp4a_us(xin9[tap], wv.w, a3);
+      }
+      const int c = cg * 16 + q * 4;
+      packed[q] = requant_u8(a0 - s_corr[c], s_bdiv[c], s_mult[c], zp_out, lo) |
+                  (requant_u8(a1 - s_corr[c + 1], s_bdiv[c + 1], s_mult[c + 1], zp_out, lo) << 8) |
+                  (requant_u8(a2 - s_corr[c + 2], s_bdiv[c + 2], s_mult[c + 2], zp_out, lo) << 16) |
+                  (requant_u8(a3 - s_corr[c + 3], s_bdiv[c + 3], s_mult[c + 3], zp_out, lo) << 24);
+    }
+    reinterpret_cast<uint4*>(out)[cg] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  }
+}
+
+// =========================================================================================================
+// Plain direct 3x3 conv, any cin % 4 == 0: one thread per (pixel, output channel).  Bring-up cross-check only.
+__global__ void conv3x3_direct_kernel(const uint8_t* __restrict__ x, uint8_t* __restrict__ y, int64_t n_img, int img,
+                                      int cin, int cout, const int8_t* __restrict__ w,
+                                      const float* __restrict__ mult, const float* __restrict__ bdiv, int zp_x,
+                                      int zp_out, int relu) {
+  const int64_t total = n_img * img * img * cout;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % cout);
+    int64_t p = i / cout;
+    const int xx = (int)(p % img);
+    p /= img;
+    const int yy = (int)(p % img);
+    const int64_t b = p / img;
+    int acc = 0;
+    for (int kh = 0; kh < 3; ++kh) {
+      const int r = yy + kh - 1;
+      if (r < 0 || r >= img) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int c = xx + kw - 1;
+        if (c < 0 || c >= img) continue;
+        const uint32_t* xp = reinterpret_cast<const uint32_t*>(x + ((b * img + r) * img + c) * (int64_t)cin);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(w + ((int64_t)co * 9 + kh * 3 + kw) * cin);
+        int raw = 0, wsum = 0;
+        for (int k = 0; k < cin / 4; ++k) {
+          const uint32_t wv = __ldg(wp + k);
+          raw = dp4a_us(__ldg(xp + k), wv, raw);
+          wsum = dp4a_us(0x01010101u, wv, wsum);
+        }
+        acc += raw - zp_x * wsum;
+      }
+    }
+    y[i] = (uint8_t)requant_u8(acc, __ldg(bdiv + co), __ldg(mult + co), zp_out, relu ? zp_out : 0);
+  }
+}
+
+// =========================================================================================================
+// Small/dynamic linear on CUDA cores: y[b][n] = epilogue( sum_k x[b][k]*w[n][k] - zp_x*wsum[n] ).
+// Tile 64 (batch) x 64 (n) per 256-thread block, K stepped 64 bytes through shared memory, 4x4 outputs per thread.
+enum LinearEpilogue { EPI_REQUANT_U8 = 0, EPI_REQUANT_DEQUANT_F32 = 1, EPI_DYNAMIC_F32 = 2 };
+
+struct LinearArgs {
+  const uint8_t* x;
+  void* y;
+  const int8_t* w;
+  const int32_t* corr;   // [n] zp_x * wsum (static) or wsum (dynamic)
+  const float* mult;     // static: requant mult[n]
+  const float* bdiv;     // static: bdiv[n]; dynamic: bias[n]
+  const float* qp;       // dynamic: device {min,max,scale,inv_scale,zp}
+  int64_t b;
+  int k, n;
+  int zp_out, relu;
+  float out_scale;       // dequant scale (EPI_REQUANT_DEQUANT_F32) or w_scale (EPI_DYNAMIC_F32)
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(256) linear_simt_kernel(const LinearArgs a) {
+  constexpr int TB = 64, TN = 64, KW = 16;  // K step = 16 words = 64 bytes
+  __shared__ uint32_t sx[TB][KW + 1];
+  __shared__ uint32_t sw[TN][KW + 1];
+  const int tid = threadIdx.x;
+  const int64_t b0 = (int64_t)blockIdx.x * TB;
+  const int n0 = blockIdx.y * TN;
+  const int tb = (tid / 16) * 4, tn = (tid % 16) * 4;
+  int acc[4][4] = {};
+  const int kwords = a.k / 4;
+  for (int k0 = 0; k0 < kwords; k0 += KW) {
+    for (int i = tid; i < TB * KW; i += 256) {
+      const int r = i / KW, c = i % KW;
+      const int64_t bb = b0 + r;
+      sx[r][c] = (bb < a.b && k0 + c < kwords)
+                     ? __ldg(reinterpret_cast<const uint32_t*>(a.x + bb * a.k) + k0 + c) : 0u;
+      const int nn = n0 + r;
+      sw[r][c] = (nn < a.n && k0 + c < kwords)
+                     ? __ldg(reinterpret_cast<const uint32_t*>(a.w + (int64_t)nn * a.k) + k0 + c) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < KW; ++c) {
+      uint32_t xv[4], wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        xv[i] = sx[tb + i][c];
+        wv[i] = sw[tn + i][c];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = dp4a_us(xv[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float s_x = 0.f;
+  int zp_dyn = 0;
+  if constexpr (EPI == EPI_DYNAMIC_F32) {
+    s_x = a.qp[2];
+    zp_dyn = (int)a.qp[4];
+  }
+  const int lo = a.relu ? a.zp_out : 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t bb = b0 + tb + i;
+    if (bb >= a.b) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nn = n0 + tn + j;
+      if (nn >= a.n) continue;
+      if constexpr (EPI == EPI_DYNAMIC_F32) {
+        // quantized::linear_dynamic: y = f32(acc) * (s_x * s_w) + bias
+        const int t = acc[i][j] - zp_dyn * __ldg(a.corr + nn);
+        float v = __fadd_rn(__fmul_rn(__int2float_rn(t), __fmul_rn(s_x, a.out_scale)), __ldg(a.bdiv + nn));
+        if (a.relu) v = fmaxf(v, 0.0f);
+        reinterpret_cast<float*>(a.y)[bb * a.n + nn] = v;
+      } else {
+        const uint32_t q =
+            requant_u8(acc[i][j] - __ldg(a.corr + nn), __ldg(a.bdiv + nn), __ldg(a.mult + nn), a.zp_out, lo);
+        if constexpr (EPI == EPI_REQUANT_U8) {
+          reinterpret_cast<uint8_t*>(a.y)[bb * a.n + nn] = (uint8_t)q;
+        } else {
+          reinterpret_cast<float*>(a.y)[bb * a.n + nn] = __fmul_rn(__int2float_rn((int)q - a.zp_out), a.out_scale);
+        }
+      }
+    }
+  }
+}
+
+template <int EPI>
+static int launch_linear(const LinearArgs& a, cudaStream_t s) {
+  dim3 grid((unsigned)((a.b + 63) / 64), (unsigned)((a.n + 63) / 64));
+  linear_simt_kernel<EPI><<<grid, 256, 0, s>>>(a);
+  return check_cuda(cudaGetLastError(), "linear_simt_kernel");
+}
+
+static int check_linear(const uint8_t* x, const void* y, int64_t b, const b200q_linear* L) {
+  B200Q_REQUIRE(L && ((x && y) || b == 0), "linear: null pointer");
+  B200Q_REQUIRE(L->k > 0 && L->k % 4 == 0 && L->n > 0, "linear: need k %% 4 == 0 (k=%d n=%d)", L->k, L->n);
+  B200Q_REQUIRE(L->w && L->corr && L->rq.mult && L->rq.bdiv, "linear: unpacked layer");
+  B200Q_REQUIRE((uintptr_t)x % 4 == 0 && (uintptr_t)L->w % 4 == 0, "linear: x and w must be 4-byte aligned");
+  return 0;
+}
+
+}  // namespace b200q
+
+using namespace b200q;
+
+static int check_conv(const void* x, const void* y, int64_t b, const b200q_conv3x3* L) {
+  B200Q_REQUIRE(L && ((x && y) || b == 0), "conv3x3: null pointer");
+  B200Q_REQUIRE(L->w && L->corr && L->rq.mult && L->rq.bdiv, "conv3x3: unpacked layer");
+  B200Q_REQUIRE(L->zp_x >= 0 && L->zp_x <= 255 && L->rq.zp_out >= 0 && L->rq.zp_out <= 255,
+                "conv3x3: zero-point out of range");
+  return 0;
+}
+
+static int conv_first_impl(const void* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, bool fused, float inv_scale,
+                           void* stream) {
+  int rc = check_conv(x, y, b, L);
+  if (rc) return rc;
+  B200Q_REQUIRE(L->cin == 4 && L->cout == C1_COUT && L->img == 32,
+                "conv3x3_first: geometry must be cin=3(padded 4), cout=64, img=32 (got %d,%d,%d)", L->cin, L->cout,
+                L->img);
+  B200Q_REQUIRE((uintptr_t)y % 16 == 0 && (uintptr_t)x % 4 == 0, "conv3x3_first: misaligned buffers");
+  if (b == 0) return 0;
+  const unsigned grid = (unsigned)(b * (L->img / C1_ROWS));
+  const uint32_t* ww = reinterpret_cast<const uint32_t*>(L->w);
+  if (fused)
+    conv1_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, ww, L->corr, L->rq.mult, L->rq.bdiv, L->zp_x,
+                                                               L->rq.zp_out, L->rq.relu, inv_scale, L->img);
+  else
+    conv1_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, ww, L->corr, L->rq.mult, L->rq.bdiv, L->zp_x,
+                                                                L->rq.zp_out, L->rq.relu, 0.f, L->img);
+  return check_cuda(cudaGetLastError(), "conv1_kernel");
+}
+
+extern "C" int b200q_conv3x3_first(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, void* stream) {
+  return conv_first_impl(x, y, b, L, false, 0.f, stream);
+}
+
+extern "C" int b200q_quantize_conv3x3_first(const float* x, uint8_t* y, int64_t b, float inv_scale,
+                                            const b200q_conv3x3* L, void* stream) {
+  return conv_first_impl(x, y, b, L, true, inv_scale, stream);
+}
+
+extern "C" int b200q_conv3x3_simt(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, void* stream) {
+  int rc = check_conv(x, y, b, L);
+  if (rc) return rc;
+  B200Q_REQUIRE(L->cin % 4 == 0 && L->cout > 0 && L->img > 0, "conv3x3_simt: need cin %% 4 == 0");
+  if (b == 0) return 0;
+  const int64_t total = b * L->img * L->img * L->cout;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)num_sms() * 32) blocks = (int64_t)num_sms() * 32;
+  conv3x3_direct_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      x, y, b, L->img, L->cin, L->cout, L->w, L->rq.mult, L->rq.bdiv, L->zp_x, L->rq.zp_out, L->rq.relu);
+  return check_cuda(cudaGetLastError(), "conv3x3_direct_kernel");
+}
+
+extern "C" int b200q_linear_simt(const uint8_t* x, uint8_t* y, int64_t b, const b200q_linear* L, void* stream) {
+  int rc = check_linear(x, y, b, L);
+  if (rc) return rc;
+  if (b == 0) return 0;
+  LinearArgs a{x, y, L->w, L->corr, L->rq.mult, L->rq.bdiv, nullptr, b, L->k, L->n, L->rq.zp_out, L->rq.relu, 0.f};
+  return launch_linear<EPI_REQUANT_U8>(a, (cudaStream_t)stream);
+}
+
+extern "C" int b200q_linear_dequant(const uint8_t* x, float* y, int64_t b, const b200q_linear* L, float out_scale,
+                                    void* stream) {
+  int rc = check_linear(x, y, b, L);
+  if (rc) return rc;
+  if (b == 0) return 0;
+  LinearArgs a{x, y, L->w, L->corr, L->rq.mult, L->rq.bdiv, nullptr, b, L->k, L->n, L->rq.zp_out, L->rq.relu,
+               out_scale};
+  return launch_linear<EPI_REQUANT_DEQUANT_F32>(a, (cudaStream_t)stream);
+}
+
+extern "C" int b200q_linear_dynamic(const float* x, float* y, int64_t b, int k, int n, const int8_t* w,
+                                    const int32_t* wsum, float w_scale, const float* bias, int relu, uint8_t* xq,
+                                    void* scratch, void* stream) {
+  B200Q_REQUIRE(x && y && w && wsum && bias && xq && scratch, "linear_dynamic: null pointer");
+  B200Q_REQUIRE(b > 0 && k > 0 && k % 4 == 0 && n > 0, "linear_dynamic: bad shape b=%lld k=%d n=%d", (long long)b, k, n);
+  B200Q_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)xq % 16 == 0 && (uintptr_t)w % 4 == 0,
+                "linear_dynamic: misaligned buffers");
+  cudaStream_t s = (cudaStream_t)stream;
+  // scratch: [0, 8208) min/max partials + counter; qparams {min,max,scale,inv_scale,zp} right after (16B aligned)
+  float* qp = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 8224);
+  int rc = launch_minmax(x, b * k, qp, scratch, s);
+  if (rc) return rc;
+  rc = launch_quantize_flat(x, xq, b * k, 0.f, 0, qp, s);
+  if (rc) return rc;
+  LinearArgs a{xq, y, w, wsum, nullptr, bias, qp, b, k, n, 0, relu, w_scale};
+  return launch_linear<EPI_DYNAMIC_F32>(a, s);
+}

@@ -1,0 +1,67 @@
+"""Device engine for the static-PTQ SimpleConvNet: packed weights + workspace + the single C-ABI forward call."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .packing import PackedStaticNet
+
+TAP_NAMES = ("quant", "conv1", "conv2", "pool1", "conv3", "conv4", "pool2", "conv5", "conv6", "pool3", "fc1", "fc2")
+TAP_SHAPES = {  # per image, NHWC (quant is NHWC4: channel 3 is padding)
+    "quant": (32, 32, 4), "conv1": (32, 32, 64), "conv2": (32, 32, 64), "pool1": (16, 16, 64),
+    "conv3": (16, 16, 128), "conv4": (16, 16, 128), "pool2": (8, 8, 128), "conv5": (8, 8, 256),
+    "conv6": (8, 8, 256), "pool3": (4, 4, 256), "fc1": (512,), "fc2": (10,),
+}
+
+
+class StaticEngine:
+    """Runs ``b200q_static_forward`` on one CUDA device.  fp32 NCHW ``[B,3,32,32]`` (CUDA) -> fp32 logits ``[B,10]``."""
+
+    def __init__(self, qparams: dict, device="cuda"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.B200QError("StaticEngine needs a CUDA device (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.lib = _lib.load()
+        self.qparams = qparams
+        with torch.cuda.device(self.device):
+            self.packed = PackedStaticNet(qparams, self.device)
+        self._ws = None
+
+    def _workspace(self, b: int) -> torch.Tensor:
+        need = int(self.lib.b200q_static_workspace_bytes(b))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, taps: bool = False):
+        if not x.is_cuda:
+            raise _lib.B200QError("StaticEngine.forward expects a CUDA tensor")
+        x = x.contiguous().float()
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, 32, 32):
+            raise _lib.B200QError(f"expected [B,3,32,32] input, got {tuple(x.shape)}")
+        b = x.shape[0]
+        with torch.cuda.device(self.device):
+            logits = torch.empty((b, 10), dtype=torch.float32, device=self.device)
+            if b == 0:
+                return (logits, {}) if taps else logits
+            ws = self._workspace(b)
+            tap_ptrs = None
+            tap_tensors = {}
+            if taps:
+                arr = (C.c_void_p * len(TAP_NAMES))()
+                for i, name in enumerate(TAP_NAMES):
+                    t = torch.empty((b,) + TAP_SHAPES[name], dtype=torch.uint8, device=self.device)
+                    tap_tensors[name] = t
+                    arr[i] = t.data_ptr()
+                tap_ptrs = arr
+            rc = self.lib.b200q_static_forward(self.packed.ptr(), x.data_ptr(), logits.data_ptr(), b, ws.data_ptr(),
+                                               ws.numel(), tap_ptrs, torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc, "static_forward")
+        return (logits, tap_tensors) if taps else logits
+
+    __call__ = forward

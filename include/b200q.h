@@ -1,0 +1,136 @@
+/*
+ * b200q.h — C ABI of the B200 (sm_100a) quantized-ConvNet hot path.
+ *
+ * Drop-in boundary for the arithmetic the reference (his0si/ConvNet-Quantization)
+ * reaches through PyTorch's QuantizedCPU / FBGEMM ops.  The reference has no FFI
+ * of its own (it is pure Python); every entry point below cites the
+ * reference call site whose ATen op it replaces.  All pointers are DEVICE pointers
+ * unless the name ends in _host; the caller owns every buffer; kernels never
+ * allocate; `stream` is a cudaStream_t passed as void*.  Return value: 0 on
+ * success, negative b200q_status otherwise (no exceptions cross this boundary).
+ *
+ * Layouts: activations uint8 NHWC; conv weights int8 [Cout][kh][kw][Cin]
+ * ("K-major", K = 9*Cin); linear weights int8 [N][K].  All zero-points refer to
+ * quint8 activations; weights are symmetric (zero-point 0), per-output-channel.
+ */
+#ifndef B200Q_H_
+#define B200Q_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum b200q_status {
+  B200Q_OK = 0,
+  B200Q_ERR_INVALID_ARG = -1,   /* bad shape / null pointer / unsupported layer geometry */
+  B200Q_ERR_CUDA = -2,          /* a CUDA runtime call failed; see b200q_last_error() */
+  B200Q_ERR_NO_DEVICE = -3,     /* no sm_100 device is current */
+  B200Q_ERR_DRIVER = -4         /* cuTensorMapEncodeTiled unavailable / failed */
+} b200q_status;
+
+/* Human-readable text of the last error raised on the calling thread. */
+const char* b200q_last_error(void);
+/* ABI version of this header (bumped on any signature change). */
+int b200q_abi_version(void);
+
+/* ---- per-output-channel requantisation constants (fbgemm semantics) ----
+ *   t = f32(acc) + bdiv[c];  t = t * mult[c];  q = clamp(rne(t) + zp_out, relu ? zp_out : 0, 255)
+ * with mult[c] = (s_x*s_w[c])/s_out and bdiv[c] = bias[c]/(s_x*s_w[c]) precomputed in fp32 on the host. */
+typedef struct b200q_requant {
+  const float* mult;      /* [N]  */
+  const float* bdiv;      /* [N]  */
+  int32_t zp_out;
+  int32_t relu;           /* 1: clamp low at zp_out (aten::relu on quint8 == max(q, zp)) */
+} b200q_requant;
+
+/* 3x3 / stride 1 / pad 1 quantized convolution layer, packed.
+ * Replaces quantized::conv2d(+aten::relu) reached from the converted conv modules
+ * (fusion list models/dynamic_ptq_model.py:289-299; layer shapes models/baseline_model.py:13-34). */
+typedef struct b200q_conv3x3 {
+  int32_t cin, cout;          /* cin in {3(padded to 4), 64, 128, 256}; cout in {64,128,256} */
+  int32_t img;                /* H == W in {32, 16, 8} */
+  int32_t zp_x;               /* input activation zero-point */
+  const int8_t*  w;           /* [cout][3][3][cin_padded] */
+  const int32_t* corr;        /* [9][cout]: zp_x * sum of w over the taps valid for border class (3*rowclass+colclass) */
+  b200q_requant rq;
+} b200q_conv3x3;
+
+/* Quantized linear layer, packed.  Replaces quantized::linear(+relu) (fc1/fc2, models/baseline_model.py:37-40). */
+typedef struct b200q_linear {
+  int32_t k, n;
+  int32_t zp_x;
+  const int8_t*  w;           /* [n][k] */
+  const int32_t* corr;        /* [n]: zp_x * sum_k w[n][k] */
+  b200q_requant rq;
+} b200q_linear;
+
+/* ---- memory-bound element-wise ops -------------------------------------------------------- */
+
+/* aten::quantize_per_tensor: fp32 NCHW [b,c,h,w] -> uint8 NHWC [b,h,w,c_pad] (channels >= c filled with zp).
+ * q = clamp(rne(x * inv_scale) + zp, 0, 255), inv_scale = 1.0f/scale computed by the caller in fp32. */
+int b200q_quantize_nchw_to_nhwc(const float* x, uint8_t* y, int64_t b, int c, int h, int w, int c_pad,
+                                float inv_scale, int zp, void* stream);
+/* Flat variant (layout preserved), n elements. */
+int b200q_quantize_flat(const float* x, uint8_t* y, int64_t n, float inv_scale, int zp, void* stream);
+/* aten::dequantize: y = f32(q - zp) * scale, n elements. */
+int b200q_dequantize(const uint8_t* q, float* y, int64_t n, float scale, int zp, void* stream);
+/* aten::relu on quint8: y = max(q, zp). */
+int b200q_relu_q(const uint8_t* q, uint8_t* y, int64_t n, int zp, void* stream);
+/* aten::quantized_max_pool2d k=2 s=2 on uint8 NHWC [b,h,w,c] -> [b,h/2,w/2,c]; c % 16 == 0. */
+int b200q_max_pool2x2_nhwc(const uint8_t* x, uint8_t* y, int64_t b, int h, int w, int c, void* stream);
+/* min/max over n fp32 values -> out[0]=min(x,0), out[1]=max(x,0); scratch >= 2*1024 floats + 1 uint32 counter (zeroed). */
+int b200q_minmax(const float* x, int64_t n, float* out2, void* scratch, void* stream);
+
+/* ---- convolutions ---------------------------------------------------------------------------- */
+
+/* Direct (CUDA-core, dp4a) 3x3 conv for the first layer (cin=3 padded to 4): uint8 NHWC4 -> uint8 NHWC. */
+int b200q_conv3x3_first(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, void* stream);
+/* Fused aten::quantize_per_tensor + first conv: fp32 NCHW [b,3,img,img] -> uint8 NHWC [b,img,img,cout]. */
+int b200q_quantize_conv3x3_first(const float* x, uint8_t* y, int64_t b, float inv_scale,
+                                 const b200q_conv3x3* L, void* stream);
+/* tcgen05 implicit-GEMM 3x3 conv (cin % 64 == 0): uint8 NHWC [b,img,img,cin] -> uint8 NHWC [b,img,img,cout]
+ * or, with pool2x2 != 0, the 2x2/2 max-pooled [b,img/2,img/2,cout] (aten::quantized_max_pool2d fused). */
+int b200q_conv3x3_tc(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, int pool2x2, void* stream);
+/* Reference-grade CUDA-core version of the same op (bring-up cross-check; not used by the net). */
+int b200q_conv3x3_simt(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, void* stream);
+
+/* ---- linear ----------------------------------------------------------------------------------- */
+
+/* tcgen05 GEMM: uint8 [b,k] x int8 [n,k]^T -> uint8 [b,n]   (k % 128 == 0, n % 64 == 0). */
+int b200q_linear_tc(const uint8_t* x, uint8_t* y, int64_t b, const b200q_linear* L, void* stream);
+/* CUDA-core version (small n, e.g. fc2): uint8 [b,k] -> uint8 [b,n]. */
+int b200q_linear_simt(const uint8_t* x, uint8_t* y, int64_t b, const b200q_linear* L, void* stream);
+/* Small linear fused with aten::dequantize (fc2 + DeQuantStub): uint8 [b,k] -> fp32 [b,n]. */
+int b200q_linear_dequant(const uint8_t* x, float* y, int64_t b, const b200q_linear* L, float out_scale, void* stream);
+
+/* quantized::linear_dynamic(x, W, reduce_range=True) (models/dynamic_ptq_model.py:302-306 -> nnqd.Linear):
+ * per-tensor min/max of x on device -> (scale, zp) on device -> quantize -> int8 GEMM -> y = f32(acc)*(s_x*s_w)+bias.
+ * x fp32 [b,k]; w int8 [n][k] per-tensor symmetric scale w_scale; wsum[n] = sum_k w; bias fp32 [n]; y fp32 [b,n].
+ * xq: scratch uint8 [b*k]; scratch: >= 2*1024 floats + 16 bytes, zero-initialised once. */
+int b200q_linear_dynamic(const float* x, float* y, int64_t b, int k, int n, const int8_t* w, const int32_t* wsum,
+                         float w_scale, const float* bias, int relu, uint8_t* xq, void* scratch, void* stream);
+
+/* ---- whole static-PTQ network ------------------------------------------------------------------ */
+
+typedef struct b200q_static_net {
+  float in_inv_scale;           /* 1.0f / QuantStub scale  */
+  int32_t in_zp;
+  b200q_conv3x3 conv[6];
+  b200q_linear fc1, fc2;
+  float out_scale;              /* fc2 output scale (DeQuantStub) ; zp is fc2.rq.zp_out */
+} b200q_static_net;
+
+/* Bytes of device workspace b200q_static_forward needs for batch b. */
+int64_t b200q_static_workspace_bytes(int64_t b);
+/* fp32 NCHW [b,3,32,32] -> fp32 logits [b,10]; restates models/baseline_model.py:58-83 on the converted model.
+ * taps (optional, may be NULL): 12 device pointers receiving the uint8 activations after
+ * quant, conv1, conv2, pool1, conv3, conv4, pool2, conv5, conv6, pool3, fc1, fc2 (NHWC) for parity tests. */
+int b200q_static_forward(const b200q_static_net* net, const float* x, float* logits, int64_t b,
+                         void* workspace, int64_t workspace_bytes, uint8_t* const* taps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200Q_H_ */

@@ -1,0 +1,112 @@
+"""ORACLE (test infrastructure only — never imported by the product path).
+
+Live CPU oracle for the quantized ``SimpleConvNet`` forward: PyTorch's own
+eager-mode static PTQ ops with ``engine='fbgemm'``.  These ATen/FBGEMM
+``QuantizedCPU`` kernels (``quantized::conv2d``, ``quantized::linear``,
+``aten::quantize_per_tensor``, ``aten::quantized_max_pool2d``, ``aten::relu``,
+``aten::dequantize``) are the third-party code the reference reaches through
+``torch.quantization`` (call sites: ``models/dynamic_ptq_model.py:289-306``,
+``models/static_ptq_model.py:28``, ``models/custom_quantization_model.py:180``);
+they are not vendored under /root/reference and the reference pins no version,
+so the de-facto pin is this image's torch 2.11.0+cu128.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import this module.
+
+Parity pin: the reference holds no golden vectors for this path,
+so the pin is (i) this live oracle, (ii) ``tests/golden/*.npz`` frozen from it
+by ``tests/golden/make_golden.py`` and (iii) the integer restatement in
+``oracle/int_ops.py`` asserted equal to (i).
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.ao.quantization import (DeQuantStub, QuantStub, convert, fuse_modules,
+                                   get_default_qconfig, prepare)
+
+# fusion list: models/dynamic_ptq_model.py:289-299, models/custom_quantization_model.py:180-190
+FUSE_LIST = [["conv1", "bn1"], ["conv2", "bn2"], ["conv3", "bn3"], ["conv4", "bn4"],
+             ["conv5", "bn5"], ["conv6", "bn6"], ["fc1", "bn7"]]
+LAYER_ORDER = ("quant", "conv1", "conv2", "pool1", "conv3", "conv4", "pool2",
+               "conv5", "conv6", "pool3", "fc1", "fc2")
+
+
+class StaticWrap(nn.Module):
+    """QuantStub -> fused SimpleConvNet -> DeQuantStub.
+
+    Forward restates ``models/baseline_model.py:58-83`` with ``reshape`` instead of
+    ``view`` (a really-quantized conv output is channels-last); dropout
+    is identity in eval mode and omitted.
+    """
+
+    def __init__(self, fused: nn.Module):
+        super().__init__()
+        self.quant = QuantStub()
+        self.m = fused
+        self.dequant = DeQuantStub()
+
+    def forward(self, x, taps: dict | None = None):
+        m = self.m
+
+        def tap(name, t):
+            if taps is not None:
+                taps[name] = t
+            return t
+
+        x = tap("quant", self.quant(x))
+        x = tap("conv1", F.relu(m.conv1(x)))
+        x = tap("conv2", F.relu(m.conv2(x)))
+        x = tap("pool1", m.pool1(x))
+        x = tap("conv3", F.relu(m.conv3(x)))
+        x = tap("conv4", F.relu(m.conv4(x)))
+        x = tap("pool2", m.pool2(x))
+        x = tap("conv5", F.relu(m.conv5(x)))
+        x = tap("conv6", F.relu(m.conv6(x)))
+        x = tap("pool3", m.pool3(x))
+        x = x.reshape(-1, 256 * 4 * 4)
+        x = tap("fc1", F.relu(m.fc1(x)))
+        x = tap("fc2", m.fc2(x))
+        return self.dequant(x)
+
+
+def build_static_oracle(fp32_net: nn.Module, calib_batches) -> nn.Module:
+    """fuse -> wrap -> prepare(fbgemm qconfig) -> calibrate -> convert.  Returns the CPU int8 model."""
+    torch.backends.quantized.engine = "fbgemm"
+    fused = fuse_modules(copy.deepcopy(fp32_net).cpu().eval(), FUSE_LIST, inplace=False)
+    w = StaticWrap(fused).eval()
+    w.qconfig = get_default_qconfig("fbgemm")
+    p = prepare(w, inplace=False)
+    with torch.no_grad():
+        for xb in calib_batches:
+            p(xb)
+    return convert(p, inplace=False).eval()
+
+
+@torch.no_grad()
+def run_static_oracle(qmodel: nn.Module, x: torch.Tensor):
+    """Returns ``(logits fp32 [B,10], taps)``; taps[name] = uint8 tensor in logical NCHW/[B,F] order."""
+    torch.backends.quantized.engine = "fbgemm"
+    taps: dict = {}
+    logits = qmodel(x.cpu(), taps)
+    return logits, {k: v.int_repr() for k, v in taps.items()}
+
+
+def extract_qparams(qmodel: nn.Module) -> dict:
+    """All integers/scales of the converted model, as plain tensors (for packing and golden files)."""
+    out = {"in_scale": float(qmodel.quant.scale), "in_zp": int(qmodel.quant.zero_point)}
+    for name in ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "fc1", "fc2"):
+        mod = getattr(qmodel.m, name)
+        w = mod.weight()
+        out[name] = {
+            "w_int8": w.int_repr().clone(),
+            "w_scales": w.q_per_channel_scales().clone(),  # float64
+            "w_zps": w.q_per_channel_zero_points().clone(),
+            "bias": mod.bias().detach().clone(),
+            "out_scale": float(mod.scale),
+            "out_zp": int(mod.zero_point),
+        }
+    return out

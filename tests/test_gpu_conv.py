@@ -1,0 +1,125 @@
+"""GPU parity (bit-exact) of the convolution / linear kernels against the numpy integer restatement."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _packed(qparams, name):
+    from convnet_quantization_b200.packing import PackedConv
+    order = ["in", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6"]
+    prev = order[order.index(name) - 1]
+    if prev == "in":
+        s, zp = qparams["in_scale"], qparams["in_zp"]
+    else:
+        s, zp = qparams[prev]["out_scale"], qparams[prev]["out_zp"]
+    return PackedConv(name, qparams[name], s, zp, "cuda"), s, zp
+
+
+def _want_conv(x_u8, s, zp, L):
+    from oracle import int_ops as IO
+    return IO.conv2d_q(x_u8, s, zp, L["w_int8"], L["w_scales"], L["bias"], L["out_scale"], L["out_zp"], relu=True)
+
+
+def _rand_u8(shape, seed):
+    return torch.randint(0, 256, shape, dtype=torch.uint8, generator=torch.Generator().manual_seed(seed))
+
+
+@pytest.mark.parametrize("b", [1, 5])
+def test_conv1_first_and_fused(qparams, qparams_np, b):
+    from convnet_quantization_b200 import ops, synth
+    from oracle import int_ops as IO
+    pc, s, zp = _packed(qparams, "conv1")
+    x = synth.images_f32(b, seed=11) * 1.5
+    xq = IO.quantize_per_tensor(x.numpy().transpose(0, 2, 3, 1), s, zp)
+    want = _want_conv(xq, s, zp, qparams_np["conv1"])
+    xq4 = ops.quantize_per_tensor(x.cuda(), s, zp, c_pad=4)
+    got = ops.conv2d_q(xq4, pc, impl="first").cpu().numpy()
+    assert np.array_equal(got, want)
+    got_fused = ops.quantize_conv2d_first(x.cuda(), s, pc).cpu().numpy()
+    assert np.array_equal(got_fused, want)
+    got_simt = ops.conv2d_q(xq4, pc, impl="simt").cpu().numpy()
+    assert np.array_equal(got_simt, want)
+
+
+@pytest.mark.parametrize("name,b", [("conv2", 2), ("conv3", 3), ("conv4", 1), ("conv5", 3), ("conv6", 2)])
+def test_conv_simt(qparams, qparams_np, name, b):
+    from convnet_quantization_b200 import ops
+    pc, s, zp = _packed(qparams, name)
+    x = _rand_u8((b, pc.img, pc.img, pc.cin), 5)
+    want = _want_conv(x.numpy(), s, zp, qparams_np[name])
+    got = ops.conv2d_q(x.cuda(), pc, impl="simt").cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", ["conv2", "conv3", "conv4", "conv5", "conv6"])
+@pytest.mark.parametrize("b", [1, 2, 3, 37, 300])
+def test_conv_tc(qparams, qparams_np, name, b):
+    """tcgen05 implicit-GEMM conv: odd batches, multi-tile-per-CTA batches, saturating inputs."""
+    from convnet_quantization_b200 import ops
+    pc, s, zp = _packed(qparams, name)
+    x = _rand_u8((b, pc.img, pc.img, pc.cin), 7 * b)
+    got = ops.conv2d_q(x.cuda(), pc, impl="tc")
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    want = _want_conv(x.numpy(), s, zp, qparams_np[name])
+    bad = got != want
+    assert not bad.any(), f"{name} b={b}: {int(bad.sum())} / {bad.size} mismatches; first at {np.argwhere(bad)[:5].tolist()}"
+
+
+@pytest.mark.parametrize("b", [1, 64, 129, 1000])
+def test_linear_tc_fc1(qparams, qparams_np, b):
+    from convnet_quantization_b200 import ops
+    from convnet_quantization_b200.packing import PackedLinear
+    from oracle import int_ops as IO
+    s, zp = qparams["conv6"]["out_scale"], qparams["conv6"]["out_zp"]
+    L = qparams_np["fc1"]
+    pl = PackedLinear("fc1", qparams["fc1"], s, zp, "cuda", relu=True, nhwc_from=(256, 4, 4))
+    x = _rand_u8((b, 4, 4, 256), b)  # NHWC activations as the engine holds them
+    want = IO.linear_q(IO.flatten_nchw(x.numpy()), s, zp, L["w_int8"], L["w_scales"], L["bias"], L["out_scale"],
+                       L["out_zp"], relu=True)
+    xf = x.reshape(b, 4096).cuda()
+    got_simt = ops.linear_q(xf, pl, impl="simt").cpu().numpy()
+    assert np.array_equal(got_simt, want)
+    got = ops.linear_q(xf, pl, impl="tc")
+    torch.cuda.synchronize()
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("b", [1, 7, 200])
+def test_fc2_and_dequant(qparams, qparams_np, b):
+    from convnet_quantization_b200 import ops
+    from convnet_quantization_b200.packing import PackedLinear
+    from oracle import int_ops as IO
+    s, zp = qparams["fc1"]["out_scale"], qparams["fc1"]["out_zp"]
+    L = qparams_np["fc2"]
+    pl = PackedLinear("fc2", qparams["fc2"], s, zp, "cuda", relu=False)
+    x = _rand_u8((b, 512), b + 1)
+    want_q = IO.linear_q(x.numpy(), s, zp, L["w_int8"], L["w_scales"], L["bias"], L["out_scale"], L["out_zp"])
+    got_q = ops.linear_q(x.cuda(), pl, impl="simt").cpu().numpy()
+    assert np.array_equal(got_q, want_q)
+    got = ops.linear_dequant(x.cuda(), pl, L["out_scale"]).cpu().numpy()
+    assert np.array_equal(got, IO.dequantize(want_q, L["out_scale"], L["out_zp"]))
+
+
+@pytest.mark.parametrize("b,k,n", [(1, 4096, 512), (33, 4096, 512), (64, 512, 10)])
+def test_linear_dynamic(b, k, n):
+    """quantized::linear_dynamic vs the live torch op (tolerance: 1e-3 relative, BASELINE north_star)."""
+    from convnet_quantization_b200 import ops
+    torch.backends.quantized.engine = "fbgemm"
+    g = torch.Generator().manual_seed(b + k)
+    lin = torch.nn.Linear(k, n)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(n, k, generator=g) * 0.05)
+        lin.bias.copy_(torch.randn(n, generator=g) * 0.1)
+    qlin = torch.ao.quantization.quantize_dynamic(torch.nn.Sequential(lin), {torch.nn.Linear}, dtype=torch.qint8)[0]
+    x = torch.randn(b, k, generator=g).abs() * 0.7
+    want = qlin(x)
+    w = qlin.weight()
+    dw = ops.DynamicLinearWeights(w.int_repr(), w.q_scale(), qlin.bias(), "cuda")
+    for _ in range(2):  # twice: scratch counter must self-reset
+        got = ops.linear_dynamic(x.cuda(), dw).cpu()
+        torch.testing.assert_close(got, want, rtol=1e-3, atol=1e-3 * float(want.abs().max()))
