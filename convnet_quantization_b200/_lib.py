@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC"]
 
 EXPORTS = (
-    "b200q_last_error", "b200q_abi_version", "b200q_quantize_nchw_to_nhwc", "b200q_quantize_flat",
+    "b200q_last_error", "b200q_abi_version", "b200q_launch_count", "b200q_quantize_nchw_to_nhwc", "b200q_quantize_flat",
     "b200q_dequantize", "b200q_relu_q", "b200q_max_pool2x2_nhwc", "b200q_minmax", "b200q_conv3x3_first",
     "b200q_quantize_conv3x3_first", "b200q_conv3x3_tc", "b200q_conv3x3_simt", "b200q_linear_tc",
     "b200q_linear_simt", "b200q_linear_dequant", "b200q_linear_dynamic", "b200q_static_workspace_bytes",
@@ -136,6 +136,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.b200q_last_error.restype = C.c_char_p
     lib.b200q_last_error.argtypes = []
     lib.b200q_abi_version.restype = C.c_int
+    lib.b200q_launch_count.restype = C.c_uint64
+    lib.b200q_launch_count.argtypes = []
     lib.b200q_static_workspace_bytes.restype = C.c_int64
     lib.b200q_static_workspace_bytes.argtypes = [C.c_int64]
     for name, args in _SIGNATURES.items():

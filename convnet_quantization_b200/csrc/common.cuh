@@ -15,6 +15,7 @@ namespace b200q {
 // ---------------------------------------------------------------- host-side error plumbing
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
+int launched(const char* what);  // after every <<<>>>: bumps b200q_launch_count(), returns the launch status
 #define B200Q_CUDA(expr) do { int _rc = ::b200q::check_cuda((expr), #expr); if (_rc) return _rc; } while (0)
 #define B200Q_REQUIRE(cond, ...) do { if (!(cond)) { ::b200q::set_error(__VA_ARGS__); return B200Q_ERR_INVALID_ARG; } } while (0)
 int num_sms();

@@ -63,13 +63,13 @@ __global__ void quantize_nchw_to_nhwc_generic_kernel(const float* __restrict__ x
 }
 
 // Flat quantize: 16 floats in (4 x float4), 16 bytes out per thread-iteration.
-// qp (optional, device): {scale, inv_scale, zp-as-float} produced by minmax_qparams — used by linear_dynamic.
+// qp (optional, device): {min, max, scale, inv_scale, zp-as-float} produced by minmax_kernel — used by linear_dynamic.
 __global__ void __launch_bounds__(256) quantize_flat_kernel(const float* __restrict__ x, uint8_t* __restrict__ y,
                                                             int64_t n, float inv_scale, int zp,
                                                             const float* __restrict__ qp) {
   if (qp != nullptr) {
-    inv_scale = qp[1];
-    zp = (int)qp[2];
+    inv_scale = qp[3];
+    zp = (int)qp[4];
   }
   const int64_t nvec = n / 16;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -259,13 +259,13 @@ int launch_minmax(const float* x, int64_t n, float* out5, void* scratch, cudaStr
   int blocks = grid_for(n / 4 + 1, 256, 4);
   if (blocks > MINMAX_MAX_BLOCKS) blocks = MINMAX_MAX_BLOCKS;
   minmax_kernel<<<blocks, 256, 0, s>>>(x, n, out5, partial, counter);
-  return check_cuda(cudaGetLastError(), "minmax_kernel");
+  return launched("minmax_kernel");
 }
 
 int launch_quantize_flat(const float* x, uint8_t* y, int64_t n, float inv_scale, int zp, const float* qp_dev,
                          cudaStream_t s) {
   quantize_flat_kernel<<<grid_for(n / 16 + 1, 256), 256, 0, s>>>(x, y, n, inv_scale, zp, qp_dev);
-  return check_cuda(cudaGetLastError(), "quantize_flat_kernel");
+  return launched("quantize_flat_kernel");
 }
 
 }  // namespace b200q
@@ -285,7 +285,7 @@ extern "C" int b200q_quantize_nchw_to_nhwc(const float* x, uint8_t* y, int64_t b
     quantize_nchw_to_nhwc_generic_kernel<<<grid_for(b * hw * c_pad, 256), 256, 0, s>>>(x, y, b, c, hw, c_pad,
                                                                                       inv_scale, zp);
   }
-  return check_cuda(cudaGetLastError(), "quantize_nchw_to_nhwc");
+  return launched("quantize_nchw_to_nhwc");
 }
 
 extern "C" int b200q_quantize_flat(const float* x, uint8_t* y, int64_t n, float inv_scale, int zp, void* stream) {
@@ -300,7 +300,7 @@ extern "C" int b200q_dequantize(const uint8_t* q, float* y, int64_t n, float sca
   B200Q_REQUIRE(((uintptr_t)q % 16 == 0) && ((uintptr_t)y % 16 == 0), "dequantize: pointers must be 16-byte aligned");
   if (n == 0) return 0;
   dequantize_kernel<<<grid_for(n / 16 + 1, 256), 256, 0, (cudaStream_t)stream>>>(q, y, n, scale, zp);
-  return check_cuda(cudaGetLastError(), "dequantize_kernel");
+  return launched("dequantize_kernel");
 }
 
 extern "C" int b200q_relu_q(const uint8_t* q, uint8_t* y, int64_t n, int zp, void* stream) {
@@ -309,7 +309,7 @@ extern "C" int b200q_relu_q(const uint8_t* q, uint8_t* y, int64_t n, int zp, voi
   B200Q_REQUIRE(zp >= 0 && zp <= 255, "relu_q: zero-point out of range");
   if (n == 0) return 0;
   relu_q_kernel<<<grid_for(n / 16 + 1, 256), 256, 0, (cudaStream_t)stream>>>(q, y, n, zp);
-  return check_cuda(cudaGetLastError(), "relu_q_kernel");
+  return launched("relu_q_kernel");
 }
 
 extern "C" int b200q_max_pool2x2_nhwc(const uint8_t* x, uint8_t* y, int64_t b, int h, int w, int c, void* stream) {
@@ -321,7 +321,7 @@ extern "C" int b200q_max_pool2x2_nhwc(const uint8_t* x, uint8_t* y, int64_t b, i
   const int64_t total = b * (h / 2) * (w / 2) * (c / 16);
   max_pool2x2_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), b, h, w, c / 16);
-  return check_cuda(cudaGetLastError(), "max_pool2x2_nhwc_kernel");
+  return launched("max_pool2x2_nhwc_kernel");
 }
 
 extern "C" int b200q_minmax(const float* x, int64_t n, float* out5, void* scratch, void* stream) {

@@ -287,7 +287,7 @@ static int launch_tc(const uint8_t* x, uint8_t* y, int64_t m_rows, const int8_t*
   const int num_tiles = num_m_tiles * C::N_TILES;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   kernel<<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(map_a, map_b, args);
-  return check_cuda(cudaGetLastError(), "igemm_tc_kernel");
+  return launched("igemm_tc_kernel");
 }
 
 }  // namespace b200q

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace b200q {
@@ -19,6 +21,14 @@ int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return 0;
   set_error("CUDA error %s (%s) at %s", cudaGetErrorName(e), cudaGetErrorString(e), what);
   return B200Q_ERR_CUDA;
+}
+
+static std::atomic<uint64_t> g_launches{0};
+
+// Every kernel launch site reports here: counts the launch and converts a launch error into a status code.
+int launched(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_cuda(cudaGetLastError(), what);
 }
 
 int num_sms() {
@@ -85,4 +95,5 @@ int encode_tensor_map(CUtensorMap* out, const void* gptr, int rank, const uint64
 }  // namespace b200q
 
 extern "C" const char* b200q_last_error(void) { return b200q::g_err; }
-extern "C" int b200q_abi_version(void) { return 1; }
+extern "C" int b200q_abi_version(void) { return 2; }
+extern "C" uint64_t b200q_launch_count(void) { return b200q::g_launches.load(std::memory_order_relaxed); }

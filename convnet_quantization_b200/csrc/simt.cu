@@ -232,7 +232,7 @@ template <int EPI>
 static int launch_linear(const LinearArgs& a, cudaStream_t s) {
   dim3 grid((unsigned)((a.b + 63) / 64), (unsigned)((a.n + 63) / 64));
   linear_simt_kernel<EPI><<<grid, 256, 0, s>>>(a);
-  return check_cuda(cudaGetLastError(), "linear_simt_kernel");
+  return launched("linear_simt_kernel");
 }
 
 static int check_linear(const uint8_t* x, const void* y, int64_t b, const b200q_linear* L) {
@@ -272,7 +272,7 @@ static int conv_first_impl(const void* x, uint8_t* y, int64_t b, const b200q_con
   else
     conv1_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, ww, L->corr, L->rq.mult, L->rq.bdiv, L->zp_x,
                                                                 L->rq.zp_out, L->rq.relu, 0.f, L->img);
-  return check_cuda(cudaGetLastError(), "conv1_kernel");
+  return launched("conv1_kernel");
 }
 
 extern "C" int b200q_conv3x3_first(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, void* stream) {
@@ -294,7 +294,7 @@ extern "C" int b200q_conv3x3_simt(const uint8_t* x, uint8_t* y, int64_t b, const
   if (blocks > (int64_t)num_sms() * 32) blocks = (int64_t)num_sms() * 32;
   conv3x3_direct_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       x, y, b, L->img, L->cin, L->cout, L->w, L->rq.mult, L->rq.bdiv, L->zp_x, L->rq.zp_out, L->rq.relu);
-  return check_cuda(cudaGetLastError(), "conv3x3_direct_kernel");
+  return launched("conv3x3_direct_kernel");
 }
 
 extern "C" int b200q_linear_simt(const uint8_t* x, uint8_t* y, int64_t b, const b200q_linear* L, void* stream) {

@@ -1,0 +1,142 @@
+"""``nn.Module`` shells around the CUDA engines, shaped so the reference's drivers can use them unchanged
+(``utils/inference_benchmark.py:19-28`` calls ``eval()/to(device)/model(data)``; ``utils/model_evaluator.py:19-33``
+calls ``eval()/cpu()/model(cpu_images)`` and ``outputs.topk`` on the result):
+
+* ``forward`` accepts fp32 NCHW ``[B,3,32,32]`` on CPU **or** CUDA and returns fp32 logits ``[B,10]`` on the input's
+  device (H2D / D2H done here when the caller hands CPU tensors);
+* ``.cpu()`` / ``.to('cpu')`` never tear the GPU engine down (the arithmetic has no CPU fallback);
+* ``.to('cuda:N')`` re-homes the engine; everything mutates in place because the driver discards ``.to()``'s result.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib, ops
+from ..engine import StaticEngine
+
+
+def _default_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.B200QError("no CUDA device: the quantized forward has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class _GpuResident(nn.Module):
+    """Common device handling: the engine lives on ``self.engine_device`` regardless of ``.cpu()``."""
+
+    quantized = True  # sniffed by utils/model_evaluator.py:25,66
+
+    def __init__(self, device=None):
+        super().__init__()
+        self.engine_device = torch.device(device) if device is not None else _default_device()
+        if self.engine_device.type != "cuda":
+            raise _lib.B200QError("engine device must be CUDA")
+        if self.engine_device.index is None:
+            self.engine_device = torch.device("cuda", torch.cuda.current_device())
+
+    def _rehome(self, device: torch.device):  # overridden
+        raise NotImplementedError
+
+    def to(self, *args, **kwargs):
+        device = kwargs.get("device", args[0] if args else None)
+        if isinstance(device, str):
+            device = torch.device(device)
+        if isinstance(device, torch.device) and device.type == "cuda":
+            if device.index is None:
+                device = torch.device("cuda", torch.cuda.current_device())
+            if device != self.engine_device:
+                self._rehome(device)
+        return self  # 'cpu' (or dtype-only) requests: nothing to move, the engine stays on its GPU
+
+    def cpu(self):
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", device) if isinstance(device, int) else (device or "cuda"))
+
+    def _run(self, x: torch.Tensor, fn):
+        if x.dtype != torch.float32:
+            x = x.float()
+        if x.is_cuda and x.device == self.engine_device:
+            return fn(x.contiguous())
+        y = fn(x.to(self.engine_device, non_blocking=True).contiguous())
+        return y.to(x.device)
+
+
+class B200StaticQuantizedNet(_GpuResident):
+    """True static-PTQ int8 ``SimpleConvNet`` (all eight layers int8, fbgemm-exact requantisation) on a B200."""
+
+    def __init__(self, qparams: dict, device=None):
+        super().__init__(device)
+        self.qparams = qparams
+        self.engine = StaticEngine(qparams, self.engine_device)
+
+    def _rehome(self, device):
+        self.engine = StaticEngine(self.qparams, device)
+        self.engine_device = device
+
+    @torch.no_grad()
+    def forward(self, x):
+        return self._run(x, self.engine.forward)
+
+    @torch.no_grad()
+    def forward_with_taps(self, x):
+        """(logits, {layer: uint8 NHWC activations}) — parity-test hook."""
+        return self.engine.forward(x.to(self.engine_device).float().contiguous(), taps=True)
+
+    def state_dict(self, *args, **kwargs):
+        """int8 weights + fp32 scales/bias, so ``get_model_size`` (torch.save of the state_dict,
+        ``models/static_ptq_model.py:36-43``) reports the quantized size."""
+        sd = {"quant.scale": torch.tensor(self.qparams["in_scale"]), "quant.zero_point": torch.tensor(self.qparams["in_zp"])}
+        for name, L in self.qparams.items():
+            if isinstance(L, dict):
+                sd[f"{name}.weight"] = L["w_int8"]
+                sd[f"{name}.weight_scales"] = L["w_scales"].float()
+                sd[f"{name}.bias"] = L["bias"]
+                sd[f"{name}.scale"] = torch.tensor(L["out_scale"])
+                sd[f"{name}.zero_point"] = torch.tensor(L["out_zp"])
+        return sd
+
+
+class B200DynamicQuantizedNet(_GpuResident):
+    """The reference's dynamic-PTQ net *as written* (SURVEY F3): ``quantize_dynamic`` only swaps ``fc1``/``fc2`` for
+    ``DynamicQuantizedLinear``; the six BN-folded convs stay fp32.  Here the convs run as fp32 ATen/cuDNN ops (TF32 off;
+    this is the tolerance path, not the product) and both linears run ``b200q_linear_dynamic`` (device-side min/max ->
+    qparams -> quantize -> int8 GEMM -> fp32)."""
+
+    def __init__(self, fused_fp32: nn.Module, fc_weights: dict, device=None):
+        super().__init__(device)
+        self._fused_cpu = fused_fp32
+        self._fc_cpu = fc_weights  # name -> (w_int8, w_scale, bias)
+        self._build(self.engine_device)
+
+    def _build(self, device):
+        self.convs = [(getattr(self._fused_cpu, f"conv{i}").weight.detach().to(device),
+                       getattr(self._fused_cpu, f"conv{i}").bias.detach().to(device)) for i in range(1, 7)]
+        self.fc = {n: ops.DynamicLinearWeights(w, s, b, device) for n, (w, s, b) in self._fc_cpu.items()}
+
+    def _rehome(self, device):
+        self._build(device)
+        self.engine_device = device
+
+    def _forward_dev(self, x):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            for i, (w, b) in enumerate(self.convs, start=1):
+                x = F.relu(F.conv2d(x, w, b, padding=1))
+                if i % 2 == 0:
+                    x = F.max_pool2d(x, 2, 2)
+        x = x.reshape(x.shape[0], -1).contiguous()
+        x = ops.linear_dynamic(x, self.fc["fc1"], relu=True)
+        return ops.linear_dynamic(x, self.fc["fc2"], relu=False)
+
+    @torch.no_grad()
+    def forward(self, x):
+        return self._run(x, self._forward_dev)
+
+    def state_dict(self, *args, **kwargs):
+        sd = {k: v for k, v in self._fused_cpu.state_dict().items() if not k.startswith(("fc1", "fc2"))}
+        for n, (w, s, b) in self._fc_cpu.items():
+            sd[f"{n}.weight"], sd[f"{n}.scale"], sd[f"{n}.bias"] = w, torch.tensor(s), b
+        return sd

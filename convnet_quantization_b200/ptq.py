@@ -41,6 +41,12 @@ def fuse_bn(fp32_net: nn.Module) -> nn.Module:
         return torch.ao.quantization.fuse_modules(net, FUSE_LIST, inplace=False)
 
 
+def fold_identity(fp32_net: nn.Module) -> nn.Module:
+    """BN folded into the preceding conv/linear for *execution* only (numerically the unfused eval-mode net up to
+    fp32 rounding); used by ``StaticPTQModel(mode="as_written")`` whose reference code does not fuse."""
+    return fuse_bn(fp32_net)
+
+
 class _CalibWrap(nn.Module):
     """QuantStub -> BN-folded SimpleConvNet -> DeQuantStub; forward = ``models/baseline_model.py:58-83``
     with ``reshape`` in place of ``view`` and dropout (identity in eval) dropped."""
@@ -61,11 +67,24 @@ class _CalibWrap(nn.Module):
         return self.dequant(m.fc2(F.relu(m.fc1(x))))
 
 
+class single_thread:
+    """Calibration runs the fp32 net on the CPU; its summation order (and with it the last ulp of the observed
+    activation ranges) depends on the intra-op thread count.  Pinning one thread makes the derived scales a function
+    of (weights, calibration images) only."""
+
+    def __enter__(self):
+        self.n = torch.get_num_threads()
+        torch.set_num_threads(1)
+
+    def __exit__(self, *exc):
+        torch.set_num_threads(self.n)
+
+
 def calibrate_static(fp32_net: nn.Module, calib_batches) -> dict:
     """Returns the static-PTQ parameter dict:
     ``{"in_scale", "in_zp", layer: {"w_int8", "w_scales"(f64), "bias"(f32), "out_scale", "out_zp"}}``."""
     select_engine()
-    with warnings.catch_warnings():
+    with warnings.catch_warnings(), single_thread():
         warnings.simplefilter("ignore")
         wrap = _CalibWrap(fuse_bn(fp32_net)).eval()
         wrap.qconfig = torch.ao.quantization.get_default_qconfig("fbgemm")

@@ -34,6 +34,9 @@ typedef enum b200q_status {
 const char* b200q_last_error(void);
 /* ABI version of this header (bumped on any signature change). */
 int b200q_abi_version(void);
+/* Number of CUDA kernels this library has launched in this process (all threads); bench.py reports the delta
+ * over its timed region as "gpu_launches". */
+uint64_t b200q_launch_count(void);
 
 /* ---- per-output-channel requantisation constants (fbgemm semantics) ----
  *   t = f32(acc) + bdiv[c];  t = t * mult[c];  q = clamp(rne(t) + zp_out, relu ? zp_out : 0, 255)

@@ -80,10 +80,32 @@ def build_static_oracle(fp32_net: nn.Module, calib_batches) -> nn.Module:
     w = StaticWrap(fused).eval()
     w.qconfig = get_default_qconfig("fbgemm")
     p = prepare(w, inplace=False)
-    with torch.no_grad():
-        for xb in calib_batches:
-            p(xb)
+    nthreads = torch.get_num_threads()
+    torch.set_num_threads(1)  # observed ranges must not depend on the fp32 summation order of a thread count
+    try:
+        with torch.no_grad():
+            for xb in calib_batches:
+                p(xb)
+    finally:
+        torch.set_num_threads(nthreads)
     return convert(p, inplace=False).eval()
+
+
+def override_activation_qparams(qmodel: nn.Module, act: dict) -> nn.Module:
+    """Replace the calibrated activation scales / zero-points of a converted model with frozen ones.
+
+    ``act`` maps ``"in"`` and each layer name to ``(scale, zero_point)``.  Calibration runs fp32 MKL-DNN kernels
+    whose last-ulp results depend on the host ISA, so golden-vector tests pin the observed ranges instead of
+    re-deriving them on whatever CPU the test runs on; everything downstream is integer-exact.
+    """
+    s, z = act["in"]
+    qmodel.quant.scale.fill_(float(s))
+    qmodel.quant.zero_point.fill_(int(z))
+    for name in ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "fc1", "fc2"):
+        s, z = act[name]
+        mod = getattr(qmodel.m, name)
+        mod.scale, mod.zero_point = float(s), int(z)
+    return qmodel
 
 
 @torch.no_grad()

@@ -69,3 +69,43 @@ def qparams_np(qparams):
 def lib():
     from convnet_quantization_b200 import _lib
     return _lib.load(build_if_missing=True)
+
+
+GOLDEN_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "convnet_golden.npz")
+_LAYERS = ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "fc1", "fc2")
+
+
+def golden_activation_qparams(g) -> dict:
+    """Frozen activation (scale, zero_point) pairs of the golden file: calibration is fp32 CPU work whose last ulp
+    depends on the host ISA, so golden comparisons pin the observed ranges (the rest is integer-exact)."""
+    act = {"in": (float(g["in_scale"]), int(g["in_zp"]))}
+    for n in _LAYERS:
+        act[n] = (float(g[f"{n}_out_scale"]), int(g[f"{n}_out_zp"]))
+    return act
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return np.load(GOLDEN_PATH)
+
+
+@pytest.fixture(scope="session")
+def golden_qparams(fp32_net, golden):
+    """Product-derived weights/bias + the golden file's activation qparams."""
+    import copy
+    from convnet_quantization_b200 import ptq, synth
+    qp = copy.deepcopy(ptq.calibrate_static(fp32_net, synth.calibration_batches()))
+    act = golden_activation_qparams(golden)
+    qp["in_scale"], qp["in_zp"] = act["in"]
+    for n in _LAYERS:
+        qp[n]["out_scale"], qp[n]["out_zp"] = act[n]
+    return qp
+
+
+@pytest.fixture(scope="session")
+def golden_oracle(fp32_net, golden):
+    """torch/fbgemm oracle with the golden file's activation qparams."""
+    from convnet_quantization_b200 import synth
+    from oracle import torch_oracle
+    q = torch_oracle.build_static_oracle(fp32_net, synth.calibration_batches())
+    return torch_oracle.override_activation_qparams(q, golden_activation_qparams(golden))

@@ -1,0 +1,142 @@
+"""Drop-in model classes on the GPU: same API as the reference's models/, driven by reference-protocol drivers."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "convnet_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def want_static(golden, oracle_model):
+    """Static-PTQ logits of the live torch/fbgemm oracle, calibrated on this host like the product's ``quantize()``
+    (the golden file's logits belong to the golden activation scales; see conftest.golden_activation_qparams)."""
+    from oracle import torch_oracle as TO
+    return TO.run_static_oracle(oracle_model, _x(golden))[0].numpy()
+
+
+@pytest.fixture(scope="module")
+def sd():
+    from convnet_quantization_b200 import synth
+    return synth.make_state_dict(0)
+
+
+def _x(golden):
+    from convnet_quantization_b200 import synth
+    return synth.normalize(torch.from_numpy(golden["x_u8"])).contiguous()
+
+
+def test_static_ptq_model_cpu_and_cuda_inputs(golden, sd, want_static):
+    from convnet_quantization_b200.models.static_ptq_model import StaticPTQModel
+    m = StaticPTQModel()
+    m.fp32_model.load_state_dict(sd)
+    q = m.quantize()  # calibration_data_loader=None -> fixed synthetic calibration set
+    assert q is m.quantized_model and hasattr(q, "quantized")
+    x = _x(golden)
+    out_cpu = q.eval().cpu()(x)                    # ModelEvaluator protocol: .cpu() then CPU images
+    assert out_cpu.device.type == "cpu"
+    assert np.array_equal(out_cpu.numpy(), want_static)
+    q.to("cuda")
+    out_gpu = q(x.cuda())                          # InferenceBenchmark(device='cuda') protocol
+    assert out_gpu.is_cuda and np.array_equal(out_gpu.cpu().numpy(), want_static)
+    assert 2.5 < m.get_model_size(q) < 4.5         # ~3.25 M int8 weights + scales
+
+
+def test_static_ptq_model_with_calibration_loader(golden, sd, want_static):
+    from convnet_quantization_b200 import synth
+    from convnet_quantization_b200.models.static_ptq_model import StaticPTQModel
+    loader = [(b, torch.zeros(b.shape[0], dtype=torch.long)) for b in synth.calibration_batches()]
+    m = StaticPTQModel()
+    m.fp32_model.load_state_dict(sd)
+    q = m.quantize(loader)
+    assert np.array_equal(q(_x(golden)).numpy(), want_static)
+
+
+def test_dynamic_ptq_model_vs_reference_class(golden, sd):
+    """Tolerance from BASELINE north_star: 1e-3 relative on logits and identical argmax."""
+    from convnet_quantization_b200.models.dynamic_ptq_model import DynamicPTQModel
+    m = DynamicPTQModel()
+    m.load_state_dict(sd)
+    m.quantize()
+    x = _x(golden)
+    got = m.eval().cpu()(x).numpy()
+    want = golden["ref_dynamic"]
+    tol = 1e-3 * np.abs(want).max()
+    np.testing.assert_allclose(got, want, rtol=1e-3, atol=tol)
+    assert np.array_equal(got.argmax(1), want.argmax(1))
+    # dynamic activation scale is per batch tensor: per-image batches are a different (also pinned) result
+    got1 = np.concatenate([m(x[i:i + 1]).numpy() for i in range(4)])
+    np.testing.assert_allclose(got1, golden["ref_dynamic_b1"], rtol=1e-3, atol=tol)
+    assert m.get_model_size() > 1.0
+
+
+def test_static_as_written_equals_dynamic_on_unfused(golden, sd):
+    from convnet_quantization_b200.models.static_ptq_model import StaticPTQModel
+    m = StaticPTQModel(mode="as_written")
+    m.fp32_model.load_state_dict(sd)
+    q = m.quantize()
+    got = q(_x(golden)).numpy()
+    # as written == quantize_dynamic on the unfused net: compare against torch's own CPU result
+    from convnet_quantization_b200.models.baseline_model import SimpleConvNet
+    ref = SimpleConvNet()
+    ref.load_state_dict(sd)
+    torch.backends.quantized.engine = "fbgemm"
+    qref = torch.ao.quantization.quantize_dynamic(ref.eval(), {torch.nn.Linear, torch.nn.Conv2d}, dtype=torch.qint8)
+    with torch.no_grad():
+        want = qref(_x(golden)).numpy()
+    np.testing.assert_allclose(got, want, rtol=2e-3, atol=2e-3 * np.abs(want).max())
+    assert np.array_equal(got.argmax(1), want.argmax(1))
+
+
+def test_fp32_and_custom_on_cuda(golden, sd):
+    from convnet_quantization_b200.models.baseline_model import SimpleConvNet
+    from convnet_quantization_b200.models.custom_quantization_model import CustomQuantizationModel
+    x = _x(golden).cuda()
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False), torch.no_grad():
+        net = SimpleConvNet()
+        net.load_state_dict(sd)
+        got = net.eval().cuda()(x).cpu().numpy()
+        cm = CustomQuantizationModel()
+        cm.load_state_dict(sd)
+        cm.quantize()
+        got_c = cm.eval().cuda()(x).cpu().numpy()
+    for g, w in ((got, golden["ref_fp32"]), (got_c, golden["ref_custom"])):
+        np.testing.assert_allclose(g, w, rtol=1e-3, atol=1e-3 * np.abs(w).max())
+        assert np.array_equal(g.argmax(1), w.argmax(1))
+
+
+def test_custom_int8_and_optimized_custom(golden, sd, want_static):
+    from convnet_quantization_b200.models.baseline_model import SimpleConvNet
+    from convnet_quantization_b200.models.custom_quantization_model import CustomQuantizationModel
+    from convnet_quantization_b200.models.optimized_custom_quantization import OptimizedCustomQuantization
+    cm = CustomQuantizationModel(mode="int8")
+    cm.load_state_dict(sd)
+    cm.quantize()
+    assert np.array_equal(cm(_x(golden)).numpy(), want_static)
+    net = SimpleConvNet()
+    net.load_state_dict(sd)
+    oq = OptimizedCustomQuantization()
+    qm = oq.quantize(net)
+    assert qm.quantized and qm.is_custom_quantized
+    assert np.array_equal(qm(_x(golden)).numpy(), want_static)
+    assert oq.get_model_size(qm) < 4.5
+
+
+def test_drivers_protocol(sd):
+    """The repo's drivers restate utils/inference_benchmark.py / utils/model_evaluator.py; run them on the GPU model."""
+    from convnet_quantization_b200 import synth
+    from convnet_quantization_b200.drivers import InferenceBenchmark, ModelEvaluator
+    from convnet_quantization_b200.models.baseline_model import SimpleConvNet
+    from convnet_quantization_b200.models.static_ptq_model import StaticPTQModel
+    net = SimpleConvNet()
+    net.load_state_dict(sd)
+    loader = synth.SyntheticLoader(256, 64, seed=5, label_model=net)
+    m = StaticPTQModel()
+    m.fp32_model.load_state_dict(sd)
+    q = m.quantize()
+    top1, top5 = ModelEvaluator(loader).evaluate_accuracy(q, verbose=False)
+    assert top1 > 60.0 and top5 >= top1  # labels are the fp32 argmax; int8 agrees on most images
+    thr = InferenceBenchmark(loader, device="cuda").measure_throughput(q, batch_size=32, num_iterations=20, verbose=False)
+    assert thr > 0

@@ -1,0 +1,81 @@
+"""Whole-network GPU parity: b200q_static_forward vs the live torch/fbgemm CPU oracle and the golden vectors —
+bit-exact uint8 activations at every layer and bit-exact fp32 logits."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "convnet_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def engine(qparams):
+    from convnet_quantization_b200.engine import StaticEngine
+    return StaticEngine(qparams, "cuda")
+
+
+def _oracle_taps_nhwc(taps):
+    out = {}
+    for k, v in taps.items():
+        a = v.numpy()
+        out[k] = a.transpose(0, 2, 3, 1) if a.ndim == 4 else a
+    return out
+
+
+@pytest.mark.parametrize("b,seed,gain", [(1, 1, 1.0), (2, 2, 1.0), (7, 3, 1.0), (64, 4, 1.0), (33, 5, 3.0)])
+def test_static_forward_taps_bit_exact(engine, oracle_model, b, seed, gain):
+    from convnet_quantization_b200 import synth
+    from oracle import torch_oracle as TO
+    x = synth.images_f32(b, seed) * gain  # gain 3: out-of-calibration, saturating activations
+    want_logits, want = TO.run_static_oracle(oracle_model, x)
+    want = _oracle_taps_nhwc(want)
+    logits, taps = engine.forward(x.cuda(), taps=True)
+    torch.cuda.synchronize()
+    for k in TO.LAYER_ORDER:
+        got = taps[k].cpu().numpy()
+        if k == "quant":
+            got = got[..., :3]
+        bad = got != want[k]
+        assert not bad.any(), f"{k}: {int(bad.sum())}/{bad.size} mismatches (b={b})"
+    assert torch.equal(logits.cpu(), want_logits)
+    # the no-taps path (fused quantize+conv1, no copies) must give the same logits
+    assert torch.equal(engine.forward(x.cuda()).cpu(), want_logits)
+
+
+def test_static_forward_matches_golden(golden_qparams):
+    from convnet_quantization_b200 import synth
+    from convnet_quantization_b200.engine import StaticEngine
+    engine = StaticEngine(golden_qparams, "cuda")
+    g = np.load(GOLDEN)
+    x = synth.normalize(torch.from_numpy(g["x_u8"])).contiguous()
+    logits, taps = engine.forward(x.cuda(), taps=True)
+    assert np.array_equal(logits.cpu().numpy(), g["static_logits"])
+    for k, t in taps.items():
+        a = t.cpu().numpy()
+        if k == "quant":
+            a = np.ascontiguousarray(a[..., :3])
+        assert hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() == str(g[f"static_{k}_sha"]), k
+
+
+def test_static_forward_large_batch_properties(engine, oracle_model):
+    """Full-size run (8192 images): per-image independence (batch composition must not matter) and spot parity."""
+    from convnet_quantization_b200 import synth
+    from oracle import torch_oracle as TO
+    n = 8192
+    x = synth.images_f32(n, seed=9).cuda()
+    big = engine.forward(x)
+    idx = torch.tensor([0, 1, 127, 128, 4095, 4096, n - 2, n - 1])
+    small = engine.forward(x[idx.cuda()].contiguous())
+    assert torch.equal(big[idx.cuda()], small)
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(0)).cuda()
+    assert torch.equal(engine.forward(x[perm].contiguous()), big[perm])
+    want, _ = TO.run_static_oracle(oracle_model, x[:256].cpu())
+    assert torch.equal(big[:256].cpu(), want)
+
+
+def test_empty_batch(engine):
+    out = engine.forward(torch.empty(0, 3, 32, 32, device="cuda"))
+    assert tuple(out.shape) == (0, 10)
