@@ -25,7 +25,7 @@ EXPORTS = (
     "b200q_dequantize", "b200q_relu_q", "b200q_max_pool2x2_nhwc", "b200q_minmax", "b200q_conv3x3_first",
     "b200q_quantize_conv3x3_first", "b200q_conv3x3_tc", "b200q_conv3x3_simt", "b200q_linear_tc",
     "b200q_linear_simt", "b200q_linear_dequant", "b200q_linear_dynamic", "b200q_static_workspace_bytes",
-    "b200q_static_forward",
+    "b200q_static_forward", "b200q_static_num_stages", "b200q_static_stage_name", "b200q_static_forward_profiled",
 )
 
 
@@ -114,6 +114,8 @@ _SIGNATURES = {
     "b200q_linear_dequant": [_P, _P, _L, C.POINTER(Linear), _F, _P],
     "b200q_linear_dynamic": [_P, _P, _L, _I, _I, _P, _P, _F, _P, _I, _P, _P, _P],
     "b200q_static_forward": [C.POINTER(StaticNet), _P, _P, _L, _P, _L, C.POINTER(C.c_void_p), _P],
+    "b200q_static_forward_profiled": [C.POINTER(StaticNet), _P, _P, _L, _P, _L, C.POINTER(C.c_float), _P],
+    "b200q_static_num_stages": [],
 }
 
 _lib = None
@@ -140,6 +142,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.b200q_launch_count.argtypes = []
     lib.b200q_static_workspace_bytes.restype = C.c_int64
     lib.b200q_static_workspace_bytes.argtypes = [C.c_int64]
+    lib.b200q_static_stage_name.restype = C.c_char_p
+    lib.b200q_static_stage_name.argtypes = [C.c_int]
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int

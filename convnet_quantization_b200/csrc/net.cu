@@ -20,8 +20,14 @@ extern "C" int64_t b200q_static_workspace_bytes(int64_t b) {
   return 2 * align_up(b * BYTES_PER_IMG, 1024) + 1024;
 }
 
-extern "C" int b200q_static_forward(const b200q_static_net* net, const float* x, float* logits, int64_t b,
-                                    void* workspace, int64_t workspace_bytes, uint8_t* const* taps, void* stream) {
+namespace {
+// One entry per kernel the forward enqueues (taps excluded); order == launch order.
+const char* const kStageNames[] = {"quant_conv1", "conv2", "pool1", "conv3", "conv4", "pool2",
+                                   "conv5",       "conv6", "pool3", "fc1",   "fc2_dequant"};
+constexpr int kNumStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
+
+int forward_impl(const b200q_static_net* net, const float* x, float* logits, int64_t b, void* workspace,
+                 int64_t workspace_bytes, uint8_t* const* taps, cudaEvent_t* ev, void* stream) {
   B200Q_REQUIRE(net && ((x && logits && workspace) || b == 0), "static_forward: null pointer");
   B200Q_REQUIRE(b >= 0, "static_forward: negative batch");
   if (b == 0) return 0;
@@ -31,32 +37,77 @@ extern "C" int b200q_static_forward(const b200q_static_net* net, const float* x,
   uint8_t* A = reinterpret_cast<uint8_t*>(align_up((int64_t)(uintptr_t)workspace, 1024));
   uint8_t* B = A + align_up(b * BYTES_PER_IMG, 1024);
   int rc;
+  int stage = 0;
 #define STEP(call) do { rc = (call); if (rc) return rc; } while (0)
+#define MARK() do { if (ev) B200Q_CUDA(cudaEventRecord(ev[stage++], s)); } while (0)
 
   if (taps && taps[0])  // QuantStub output is only materialised when a parity test asks for it
     STEP(b200q_quantize_nchw_to_nhwc(x, taps[0], b, 3, 32, 32, 4, net->in_inv_scale, net->in_zp, stream));
+  MARK();
   STEP(b200q_quantize_conv3x3_first(x, A, b, net->in_inv_scale, &net->conv[0], stream));
+  MARK();
   STEP(copy_tap(taps, 1, A, b * 65536, s));
   STEP(b200q_conv3x3_tc(A, B, b, &net->conv[1], 0, stream));
+  MARK();
   STEP(copy_tap(taps, 2, B, b * 65536, s));
   STEP(b200q_max_pool2x2_nhwc(B, A, b, 32, 32, 64, stream));
+  MARK();
   STEP(copy_tap(taps, 3, A, b * 16384, s));
   STEP(b200q_conv3x3_tc(A, B, b, &net->conv[2], 0, stream));
+  MARK();
   STEP(copy_tap(taps, 4, B, b * 32768, s));
   STEP(b200q_conv3x3_tc(B, A, b, &net->conv[3], 0, stream));
+  MARK();
   STEP(copy_tap(taps, 5, A, b * 32768, s));
   STEP(b200q_max_pool2x2_nhwc(A, B, b, 16, 16, 128, stream));
+  MARK();
   STEP(copy_tap(taps, 6, B, b * 8192, s));
   STEP(b200q_conv3x3_tc(B, A, b, &net->conv[4], 0, stream));
+  MARK();
   STEP(copy_tap(taps, 7, A, b * 16384, s));
   STEP(b200q_conv3x3_tc(A, B, b, &net->conv[5], 0, stream));
+  MARK();
   STEP(copy_tap(taps, 8, B, b * 16384, s));
   STEP(b200q_max_pool2x2_nhwc(B, A, b, 8, 8, 256, stream));
+  MARK();
   STEP(copy_tap(taps, 9, A, b * 4096, s));
   STEP(b200q_linear_tc(A, B, b, &net->fc1, stream));
+  MARK();
   STEP(copy_tap(taps, 10, B, b * 512, s));
   if (taps && taps[11]) STEP(b200q_linear_simt(B, taps[11], b, &net->fc2, stream));
   STEP(b200q_linear_dequant(B, logits, b, &net->fc2, net->out_scale, stream));
+  MARK();
 #undef STEP
+#undef MARK
+  return 0;
+}
+}  // namespace
+
+extern "C" int b200q_static_forward(const b200q_static_net* net, const float* x, float* logits, int64_t b,
+                                    void* workspace, int64_t workspace_bytes, uint8_t* const* taps, void* stream) {
+  return forward_impl(net, x, logits, b, workspace, workspace_bytes, taps, nullptr, stream);
+}
+
+extern "C" int b200q_static_num_stages(void) { return kNumStages; }
+extern "C" const char* b200q_static_stage_name(int i) { return (i >= 0 && i < kNumStages) ? kStageNames[i] : ""; }
+
+extern "C" int b200q_static_forward_profiled(const b200q_static_net* net, const float* x, float* logits, int64_t b,
+                                             void* workspace, int64_t workspace_bytes, float* stage_ms_host,
+                                             void* stream) {
+  B200Q_REQUIRE(stage_ms_host != nullptr, "static_forward_profiled: null stage_ms_host");
+  static thread_local cudaEvent_t ev[kNumStages + 1];
+  static thread_local int ev_device = -1;
+  int dev = -1;
+  B200Q_CUDA(cudaGetDevice(&dev));
+  if (ev_device != dev) {  // events belong to a device: (re)create on first use per thread/device
+    for (int i = 0; i <= kNumStages; ++i) B200Q_CUDA(cudaEventCreate(&ev[i]));
+    ev_device = dev;
+  }
+  for (int i = 0; i < kNumStages; ++i) stage_ms_host[i] = 0.f;
+  if (b == 0) return 0;
+  int rc = forward_impl(net, x, logits, b, workspace, workspace_bytes, nullptr, ev, stream);
+  if (rc) return rc;
+  B200Q_CUDA(cudaEventSynchronize(ev[kNumStages]));
+  for (int i = 0; i < kNumStages; ++i) B200Q_CUDA(cudaEventElapsedTime(&stage_ms_host[i], ev[i], ev[i + 1]));
   return 0;
 }

@@ -65,3 +65,22 @@ class StaticEngine:
         return (logits, tap_tensors) if taps else logits
 
     __call__ = forward
+
+    def stage_names(self):
+        return [self.lib.b200q_static_stage_name(i).decode() for i in range(self.lib.b200q_static_num_stages())]
+
+    @torch.no_grad()
+    def forward_profiled(self, x: torch.Tensor):
+        """(logits, {stage: ms}) — one forward with a CUDA event between kernels (measurement hook; synchronises)."""
+        x = x.contiguous().float()
+        b = x.shape[0]
+        n = self.lib.b200q_static_num_stages()
+        ms = (C.c_float * n)()
+        with torch.cuda.device(self.device):
+            logits = torch.empty((b, 10), dtype=torch.float32, device=self.device)
+            ws = self._workspace(b)
+            rc = self.lib.b200q_static_forward_profiled(self.packed.ptr(), x.data_ptr(), logits.data_ptr(), b,
+                                                        ws.data_ptr(), ws.numel(), ms,
+                                                        torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc, "static_forward_profiled")
+        return logits, dict(zip(self.stage_names(), (float(v) for v in ms)))

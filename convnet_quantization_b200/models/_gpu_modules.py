@@ -121,13 +121,18 @@ class B200DynamicQuantizedNet(_GpuResident):
         self._build(device)
         self.engine_device = device
 
-    def _forward_dev(self, x):
+    @torch.no_grad()
+    def features(self, x):
+        """fp32 conv stack (BN folded) -> ``[B,4096]`` in the reference's NCHW flatten order."""
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
             for i, (w, b) in enumerate(self.convs, start=1):
                 x = F.relu(F.conv2d(x, w, b, padding=1))
                 if i % 2 == 0:
                     x = F.max_pool2d(x, 2, 2)
-        x = x.reshape(x.shape[0], -1).contiguous()
+        return x.reshape(x.shape[0], -1).contiguous()
+
+    def _forward_dev(self, x):
+        x = self.features(x)
         x = ops.linear_dynamic(x, self.fc["fc1"], relu=True)
         return ops.linear_dynamic(x, self.fc["fc2"], relu=False)
 

@@ -133,6 +133,14 @@ int64_t b200q_static_workspace_bytes(int64_t b);
 int b200q_static_forward(const b200q_static_net* net, const float* x, float* logits, int64_t b,
                          void* workspace, int64_t workspace_bytes, uint8_t* const* taps, void* stream);
 
+/* Measurement hook (bench.py roofline): the same forward with a CUDA event recorded on `stream` before every layer
+ * kernel and after the last one; synchronises on the last event and writes b200q_static_num_stages() per-kernel
+ * durations in milliseconds to stage_ms_host (HOST memory).  Stage i is named b200q_static_stage_name(i). */
+int b200q_static_num_stages(void);
+const char* b200q_static_stage_name(int i);
+int b200q_static_forward_profiled(const b200q_static_net* net, const float* x, float* logits, int64_t b,
+                                  void* workspace, int64_t workspace_bytes, float* stage_ms_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
