@@ -16,8 +16,10 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libb200q.so"
 BUILD_DIR = PKG_DIR / "build"
-SOURCES = ("runtime.cu", "elementwise.cu", "simt.cu", "igemm_tc.cu", "net.cu")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+SOURCES = ("runtime.cu", "elementwise.cu", "simt.cu", "igemm_tc.cu", "conv_halo.cu", "net.cu")
+# -fmad=false: the requantisation is specified as separately rounded fp32 add / mul; ptxas was
+# seen contracting even explicit mul.rn.f32x2 + add.rn.f32x2 pairs into FFMA2, which changes the rounding.
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC"]
 
 EXPORTS = (
@@ -79,7 +81,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 # ------------------------------------------------------------------ C structs (mirror include/b200q.h)
 class Requant(C.Structure):
-    _fields_ = [("mult", C.c_void_p), ("bdiv", C.c_void_p), ("zp_out", C.c_int32), ("relu", C.c_int32)]
+    _fields_ = [("mult", C.c_void_p), ("bdiv", C.c_void_p), ("zp_out", C.c_int32), ("relu", C.c_int32),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
+
+
+RQ_BOUNDED = 1  # B200Q_RQ_BOUNDED
+RQ_ACC22 = 2    # B200Q_RQ_ACC22
 
 
 class Conv3x3(C.Structure):

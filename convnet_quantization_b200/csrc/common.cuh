@@ -19,6 +19,9 @@ int launched(const char* what);  // after every <<<>>>: bumps b200q_launch_count
 #define B200Q_CUDA(expr) do { int _rc = ::b200q::check_cuda((expr), #expr); if (_rc) return _rc; } while (0)
 #define B200Q_REQUIRE(cond, ...) do { if (!(cond)) { ::b200q::set_error(__VA_ARGS__); return B200Q_ERR_INVALID_ARG; } } while (0)
 int num_sms();
+// conv_halo.cu: halo-resident kernel for the cin=64 layers; returns 1 when the geometry is not covered
+int conv3x3_halo_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, bool pool, cudaStream_t s,
+                          int* rc);
 
 // ---------------------------------------------------------------- exact fbgemm requantisation
 // t = f32(acc) + bdiv; t = t * mult; q = clamp(rne(t) + zp, lo, 255).  Intrinsics forbid FMA contraction
@@ -30,6 +33,126 @@ __device__ __forceinline__ uint32_t requant_u8(int acc, float bdiv, float mult, 
   t = fminf(fmaxf(t, -1024.0f), 1024.0f);
   int q = __float2int_rn(t) + zp;
   return (uint32_t)max(lo, min(q, 255));
+}
+
+// ---- fast requantisation (no I2F/F2I: on sm_100 the conversion pipe issues 16 lanes/clk/SM, 8x slower than FADD) --------
+// Bit-identical to requant_u8 whenever |acc| < 2^22 and |t| < 2^22, using round-to-nearest-even of the fp32 adder itself:
+//   f32(acc)  = as_float(acc + 0x4B400000) - 12582912.0f            (exact: 1.5*2^23 + acc is representable)
+//   rne(t)    = as_int(t + 12582912.0f) - 0x4B400000                (ulp of [2^23, 2^24) is 1)
+// Callers fold "-corr" into the first integer add and "+zp" into the last one, test the range with one LOP3 per
+// element (requant_magic_range_bits) and fall back to requant_u8 for the whole chunk when any lane is out of range.
+constexpr uint32_t MAGIC_BITS = 0x4B400000u;  // as_uint(12582912.0f) = 1.5 * 2^23
+constexpr float MAGIC_F = 12582912.0f;
+
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t u2_pack(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void u2_unpack(uint64_t v, uint32_t& lo, uint32_t& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+// Packed fp32 pairs (sm_100 FADD2 / FMUL2): IEEE round-to-nearest-even per lane, no contraction possible.
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// d = bytes {sat_u8(b), sat_u8(a), c[7:0], c[15:8]} (low to high): one I2IP.U8.S32.SAT
+__device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c) {
+  uint32_t d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// Four output channels of one pixel.  acc: raw s32 accumulators; cm = MAGIC_BITS - corr (per channel, per border class);
+// zp_sub = zp_out - MAGIC_BITS; lo = lower clamp (zp_out with ReLU, else 0).  `bad` accumulates range-check bits (see above) when
+// CHECK; callers that know |acc - corr| < 2^22 statically (B200Q_RQ_ACC22) skip the test.
+// The last add is scalar on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with -fmad=false),
+// which would round t*mult + magic once instead of twice.
+template <bool CHECK>
+__device__ __forceinline__ uint32_t requant4_magic(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, const int4 cm,
+                                                   const float4 bd, const float4 mu, int zp_sub, int lo,
+                                                   uint32_t& bad) {
+  const uint32_t m0 = a0 + (uint32_t)cm.x, m1 = a1 + (uint32_t)cm.y;
+  const uint32_t m2 = a2 + (uint32_t)cm.z, m3 = a3 + (uint32_t)cm.w;
+  if constexpr (CHECK) {
+    bad |= (m0 ^ 0x4B000000u);
+    bad |= (m1 ^ 0x4B000000u);
+    bad |= (m2 ^ 0x4B000000u);
+    bad |= (m3 ^ 0x4B000000u);
+  }
+  const uint64_t neg_magic = f2_pack(-MAGIC_F, -MAGIC_F);
+  uint64_t t01 = f2_add(u2_pack(m0, m1), neg_magic);
+  uint64_t t23 = f2_add(u2_pack(m2, m3), neg_magic);
+  t01 = f2_mul(f2_add(t01, f2_pack(bd.x, bd.y)), f2_pack(mu.x, mu.y));
+  t23 = f2_mul(f2_add(t23, f2_pack(bd.z, bd.w)), f2_pack(mu.z, mu.w));
+  uint32_t r0, r1, r2, r3;
+  u2_unpack(t01, r0, r1);
+  u2_unpack(t23, r2, r3);
+  // max(x + zp_sub, lo) is one VIADDMNMX; the upper clamp (and the pack) is the saturating I2IP.  (__vmaxu4 on the
+  // packed word is emulated with ~7 instructions on sm_100.)
+  const int q0 = max(__float_as_int(__fadd_rn(__uint_as_float(r0), MAGIC_F)) + zp_sub, lo);
+  const int q1 = max(__float_as_int(__fadd_rn(__uint_as_float(r1), MAGIC_F)) + zp_sub, lo);
+  const int q2 = max(__float_as_int(__fadd_rn(__uint_as_float(r2), MAGIC_F)) + zp_sub, lo);
+  const int q3 = max(__float_as_int(__fadd_rn(__uint_as_float(r3), MAGIC_F)) + zp_sub, lo);
+  const uint32_t hi = pack_sat_u8(q3, q2, 0u);
+  return pack_sat_u8(q1, q0, hi);
+}
+// true when any accumulated range-check bit says |acc - corr| >= 2^22
+__device__ __forceinline__ bool requant_magic_out_of_range(uint32_t bad) { return (bad >> 23) != 0u; }
+
+// 32 consecutive output channels of one pixel (one tcgen05.ld 32x32b.x32 worth): v -> 8 packed words.
+// cm: this pixel's border-class row of (MAGIC_BITS - corr), bd/mu: bdiv / mult, all at the chunk's first channel
+// (shared memory, or register arrays after inlining).  `fast` = layer flagged B200Q_RQ_BOUNDED.
+template <bool CHECK>
+__device__ __forceinline__ void requant_chunk32(const uint32_t (&v)[32], const int4* cm, const float4* bd, const float4* mu,
+                                                bool fast, int zp_out, int lo, uint32_t (&packed)[8]) {
+  const int zp_sub = zp_out - (int)MAGIC_BITS;
+  uint32_t bad = 0;
+  if (fast) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      packed[g] = requant4_magic<CHECK>(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], cm[g], bd[g], mu[g], zp_sub,
+                                        lo, bad);
+  }
+  if (!fast || (CHECK && __any_sync(0xffffffffu, requant_magic_out_of_range(bad)))) {
+    // exact conversion-pipe form (rare: |acc| >= 2^22, or constants not flagged as bounded)
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int4 c = cm[g];
+      const float4 b = bd[g], m = mu[g];
+      packed[g] = requant_u8((int)(v[4 * g + 0] + (uint32_t)c.x - MAGIC_BITS), b.x, m.x, zp_out, lo) |
+                  (requant_u8((int)(v[4 * g + 1] + (uint32_t)c.y - MAGIC_BITS), b.y, m.y, zp_out, lo) << 8) |
+                  (requant_u8((int)(v[4 * g + 2] + (uint32_t)c.z - MAGIC_BITS), b.z, m.z, zp_out, lo) << 16) |
+                  (requant_u8((int)(v[4 * g + 3] + (uint32_t)c.w - MAGIC_BITS), b.w, m.w, zp_out, lo) << 24);
+    }
+  }
+}
+
+// Per-byte max of four packed uint8x4 words.  sm_100 has no native byte SIMD max (__vmaxu4 is emulated with ~7
+// instructions per pair); 16-bit lanes are native, so split even/odd bytes (PRMT), reduce with max.u16x2, re-interleave.
+__device__ __forceinline__ uint32_t max_u16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("max.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t max4_u8x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  const uint32_t e = max_u16x2(max_u16x2(__byte_perm(a, 0, 0x4240), __byte_perm(b, 0, 0x4240)),
+                               max_u16x2(__byte_perm(c, 0, 0x4240), __byte_perm(d, 0, 0x4240)));
+  const uint32_t o = max_u16x2(max_u16x2(__byte_perm(a, 0, 0x4341), __byte_perm(b, 0, 0x4341)),
+                               max_u16x2(__byte_perm(c, 0, 0x4341), __byte_perm(d, 0, 0x4341)));
+  return __byte_perm(e, o, 0x6240);
 }
 
 __device__ __forceinline__ uint32_t quantize_u8(float x, float inv_scale, int zp) {
@@ -67,14 +190,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the hint expires, whichever is first; a long
+// hint keeps idle producer / MMA threads from burning issue slots the epilogue warps of the same sub-partition need.
+constexpr uint32_t MBAR_SUSPEND_HINT_NS = 200000u;
 __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS)
       : "memory");
   return ok;
 }

@@ -146,10 +146,10 @@ __global__ void __launch_bounds__(256) max_pool2x2_nhwc_kernel(const uint4* __re
     const int64_t r1 = r0 + (int64_t)w * c16;
     const uint4 a = __ldg(x + r0), b = __ldg(x + r0 + c16), c = __ldg(x + r1), d = __ldg(x + r1 + c16);
     uint4 o;
-    o.x = __vmaxu4(__vmaxu4(a.x, b.x), __vmaxu4(c.x, d.x));
-    o.y = __vmaxu4(__vmaxu4(a.y, b.y), __vmaxu4(c.y, d.y));
-    o.z = __vmaxu4(__vmaxu4(a.z, b.z), __vmaxu4(c.z, d.z));
-    o.w = __vmaxu4(__vmaxu4(a.w, b.w), __vmaxu4(c.w, d.w));
+    o.x = max4_u8x4(a.x, b.x, c.x, d.x);
+    o.y = max4_u8x4(a.y, b.y, c.y, d.y);
+    o.z = max4_u8x4(a.z, b.z, c.z, d.z);
+    o.w = max4_u8x4(a.w, b.w, c.w, d.w);
     y[i] = o;
   }
 }

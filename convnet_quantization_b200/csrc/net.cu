@@ -21,11 +21,13 @@ extern "C" int64_t b200q_static_workspace_bytes(int64_t b) {
 }
 
 namespace {
-// One entry per kernel the forward enqueues (taps excluded); order == launch order.
-const char* const kStageNames[] = {"quant_conv1", "conv2", "pool1", "conv3", "conv4", "pool2",
-                                   "conv5",       "conv6", "pool3", "fc1",   "fc2_dequant"};
+// One entry per kernel the fused forward enqueues; order == launch order.
+const char* const kStageNames[] = {"quant_conv1", "conv2_pool", "conv3", "conv4_pool",
+                                   "conv5",       "conv6_pool", "fc1",   "fc2_dequant"};
 constexpr int kNumStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
 
+// taps == nullptr: production path, 2x2 max-pools fused into the conv2/conv4/conv6 epilogues (8 kernels).
+// taps != nullptr: parity path, every reference op materialised (unfused convs + stand-alone pools) and copied out.
 int forward_impl(const b200q_static_net* net, const float* x, float* logits, int64_t b, void* workspace,
                  int64_t workspace_bytes, uint8_t* const* taps, cudaEvent_t* ev, void* stream) {
   B200Q_REQUIRE(net && ((x && logits && workspace) || b == 0), "static_forward: null pointer");
@@ -41,42 +43,50 @@ int forward_impl(const b200q_static_net* net, const float* x, float* logits, int
 #define STEP(call) do { rc = (call); if (rc) return rc; } while (0)
 #define MARK() do { if (ev) B200Q_CUDA(cudaEventRecord(ev[stage++], s)); } while (0)
 
-  if (taps && taps[0])  // QuantStub output is only materialised when a parity test asks for it
-    STEP(b200q_quantize_nchw_to_nhwc(x, taps[0], b, 3, 32, 32, 4, net->in_inv_scale, net->in_zp, stream));
-  MARK();
+  if (taps == nullptr) {
+    MARK();
+    STEP(b200q_quantize_conv3x3_first(x, A, b, net->in_inv_scale, &net->conv[0], stream));
+    MARK();
+    STEP(b200q_conv3x3_tc(A, B, b, &net->conv[1], 1, stream));  // -> [b,16,16,64]
+    MARK();
+    STEP(b200q_conv3x3_tc(B, A, b, &net->conv[2], 0, stream));  // -> [b,16,16,128]
+    MARK();
+    STEP(b200q_conv3x3_tc(A, B, b, &net->conv[3], 1, stream));  // -> [b,8,8,128]
+    MARK();
+    STEP(b200q_conv3x3_tc(B, A, b, &net->conv[4], 0, stream));  // -> [b,8,8,256]
+    MARK();
+    STEP(b200q_conv3x3_tc(A, B, b, &net->conv[5], 1, stream));  // -> [b,4,4,256]
+    MARK();
+    STEP(b200q_linear_tc(B, A, b, &net->fc1, stream));
+    MARK();
+    STEP(b200q_linear_dequant(A, logits, b, &net->fc2, net->out_scale, stream));
+    MARK();
+    return 0;
+  }
+
+  if (taps[0]) STEP(b200q_quantize_nchw_to_nhwc(x, taps[0], b, 3, 32, 32, 4, net->in_inv_scale, net->in_zp, stream));
   STEP(b200q_quantize_conv3x3_first(x, A, b, net->in_inv_scale, &net->conv[0], stream));
-  MARK();
   STEP(copy_tap(taps, 1, A, b * 65536, s));
   STEP(b200q_conv3x3_tc(A, B, b, &net->conv[1], 0, stream));
-  MARK();
   STEP(copy_tap(taps, 2, B, b * 65536, s));
   STEP(b200q_max_pool2x2_nhwc(B, A, b, 32, 32, 64, stream));
-  MARK();
   STEP(copy_tap(taps, 3, A, b * 16384, s));
   STEP(b200q_conv3x3_tc(A, B, b, &net->conv[2], 0, stream));
-  MARK();
   STEP(copy_tap(taps, 4, B, b * 32768, s));
   STEP(b200q_conv3x3_tc(B, A, b, &net->conv[3], 0, stream));
-  MARK();
   STEP(copy_tap(taps, 5, A, b * 32768, s));
   STEP(b200q_max_pool2x2_nhwc(A, B, b, 16, 16, 128, stream));
-  MARK();
   STEP(copy_tap(taps, 6, B, b * 8192, s));
   STEP(b200q_conv3x3_tc(B, A, b, &net->conv[4], 0, stream));
-  MARK();
   STEP(copy_tap(taps, 7, A, b * 16384, s));
   STEP(b200q_conv3x3_tc(A, B, b, &net->conv[5], 0, stream));
-  MARK();
   STEP(copy_tap(taps, 8, B, b * 16384, s));
   STEP(b200q_max_pool2x2_nhwc(B, A, b, 8, 8, 256, stream));
-  MARK();
   STEP(copy_tap(taps, 9, A, b * 4096, s));
   STEP(b200q_linear_tc(A, B, b, &net->fc1, stream));
-  MARK();
   STEP(copy_tap(taps, 10, B, b * 512, s));
-  if (taps && taps[11]) STEP(b200q_linear_simt(B, taps[11], b, &net->fc2, stream));
+  if (taps[11]) STEP(b200q_linear_simt(B, taps[11], b, &net->fc2, stream));
   STEP(b200q_linear_dequant(B, logits, b, &net->fc2, net->out_scale, stream));
-  MARK();
 #undef STEP
 #undef MARK
   return 0;

@@ -34,6 +34,28 @@ def requant_constants(s_x: float, w_scales: torch.Tensor, bias: torch.Tensor, s_
     return mult.contiguous(), bdiv.contiguous()
 
 
+def acc_bound(w_int8: torch.Tensor, zp_x: int) -> int:
+    """Largest |sum_k (x_k - zp_x) * w_k| any uint8 input can produce, over output channels."""
+    w = w_int8.detach().cpu().to(torch.int64).reshape(w_int8.shape[0], -1)
+    pos, neg = w.clamp(min=0).sum(1), (-w).clamp(min=0).sum(1)
+    hi = (255 - zp_x) * pos + zp_x * neg
+    lo = zp_x * pos + (255 - zp_x) * neg
+    return int(torch.maximum(hi, lo).max())
+
+
+def requant_flags(mult: torch.Tensor, bdiv: torch.Tensor, w_int8: torch.Tensor, zp_x: int) -> int:
+    """``B200Q_RQ_BOUNDED`` when every channel satisfies the bound under which the conversion-free requantisation of
+    the tensor-core epilogue is exact, ``B200Q_RQ_ACC22`` when no input can push an accumulator past 2^22
+    (``include/b200q.h``)."""
+    flags = 0
+    if bool((mult >= 0).all() and (mult <= 0.5).all() and (bdiv.abs() <= 2.0 ** 21).all()
+            and torch.isfinite(mult).all() and torch.isfinite(bdiv).all()):
+        flags |= _lib.RQ_BOUNDED
+    if acc_bound(w_int8, zp_x) < 2 ** 22:
+        flags |= _lib.RQ_ACC22
+    return flags
+
+
 def conv_border_corr(w_int8: torch.Tensor, zp_x: int) -> torch.Tensor:
     """``corr[3*rc+cc][co]``: rc/cc = 0 first row/col, 1 interior, 2 last row/col."""
     wsum_tap = w_int8.to(torch.int64).sum(dim=1)  # [Cout, 3, 3]
@@ -61,7 +83,8 @@ class PackedConv:
         self.corr = conv_border_corr(w, zp_x).to(device)
         self.mult, self.bdiv = mult.to(device), bdiv.to(device)
         self.c = _lib.Conv3x3(cin_p, cout, img, self.zp_x, self.w.data_ptr(), self.corr.data_ptr(),
-                              _lib.Requant(self.mult.data_ptr(), self.bdiv.data_ptr(), self.zp_out, int(relu)))
+                              _lib.Requant(self.mult.data_ptr(), self.bdiv.data_ptr(), self.zp_out, int(relu),
+                                           requant_flags(mult, bdiv, w, zp_x), 0))
 
     def ptr(self):
         return C.byref(self.c)
@@ -81,7 +104,8 @@ class PackedLinear:
         self.corr = (w.to(torch.int64).sum(dim=1) * int(zp_x)).to(torch.int32).contiguous().to(device)
         self.mult, self.bdiv = mult.to(device), bdiv.to(device)
         self.c = _lib.Linear(k, n, self.zp_x, self.w.data_ptr(), self.corr.data_ptr(),
-                             _lib.Requant(self.mult.data_ptr(), self.bdiv.data_ptr(), self.zp_out, int(relu)))
+                             _lib.Requant(self.mult.data_ptr(), self.bdiv.data_ptr(), self.zp_out, int(relu),
+                                          requant_flags(mult, bdiv, w, zp_x), 0))
 
     def ptr(self):
         return C.byref(self.c)

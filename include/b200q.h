@@ -46,7 +46,16 @@ typedef struct b200q_requant {
   const float* bdiv;      /* [N]  */
   int32_t zp_out;
   int32_t relu;           /* 1: clamp low at zp_out (aten::relu on quint8 == max(q, zp)) */
+  int32_t flags;          /* B200Q_RQ_* */
+  int32_t reserved;
 } b200q_requant;
+/* Caller guarantees 0 <= mult[c] <= 0.5 and |bdiv[c]| <= 2^21 for every channel.  The tensor-core kernels then use a
+ * conversion-free formulation of the same arithmetic (bit-identical; accumulators outside +-2^22 are detected at run
+ * time and take the I2F/F2I form).  Without the flag the I2F/F2I form is always used. */
+#define B200Q_RQ_BOUNDED 1
+/* Caller guarantees |acc - corr| < 2^22 for every possible uint8 input (a bound on the layer's weights, see
+ * packing.acc_bound): lets the N=64 kernels skip the per-element run-time range test. */
+#define B200Q_RQ_ACC22 2
 
 /* 3x3 / stride 1 / pad 1 quantized convolution layer, packed.
  * Replaces quantized::conv2d(+aten::relu) reached from the converted conv modules

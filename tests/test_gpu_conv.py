@@ -123,3 +123,66 @@ def test_linear_dynamic(b, k, n):
     for _ in range(2):  # twice: scratch counter must self-reset
         got = ops.linear_dynamic(x.cuda(), dw).cpu()
         torch.testing.assert_close(got, want, rtol=1e-3, atol=1e-3 * float(want.abs().max()))
+
+
+@pytest.mark.parametrize("name", ["conv2", "conv4", "conv6"])
+@pytest.mark.parametrize("b", [1, 3, 150])
+def test_conv_tc_fused_pool(qparams, qparams_np, name, b):
+    """conv + aten::quantized_max_pool2d fused in the epilogue == pooling the oracle's conv output."""
+    from convnet_quantization_b200 import ops
+    from oracle import int_ops as IO
+    pc, s, zp = _packed(qparams, name)
+    x = _rand_u8((b, pc.img, pc.img, pc.cin), 3 * b + 1)
+    got = ops.conv2d_q(x.cuda(), pc, pool2x2=True, impl="tc")
+    torch.cuda.synchronize()
+    want = IO.max_pool2x2(_want_conv(x.numpy(), s, zp, qparams_np[name]))
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def _stress_layer(name, qparams, huge):
+    """Same geometry, adversarial constants: per-channel single-signed +-127 weights (|acc| up to ~7e7, far beyond
+    2^22) or a large multiplier."""
+    import copy
+    L = copy.deepcopy(qparams[name])
+    if huge:
+        w = L["w_int8"]
+        g = torch.Generator().manual_seed(17)
+        sign = (torch.randint(0, 2, (w.shape[0], 1, 1, 1), generator=g) * 2 - 1).to(torch.int8)
+        L["w_int8"] = (torch.randint(100, 128, w.shape, generator=g).to(torch.int8) * sign)
+    return L
+
+
+@pytest.mark.parametrize("name", ["conv2", "conv6"])
+@pytest.mark.parametrize("mode", ["huge_acc", "big_mult"])
+def test_conv_tc_requant_fallback_paths(qparams, name, mode):
+    """The conversion-free epilogue must hand over to the exact I2F/F2I form (run-time range test, or the BOUNDED flag
+    withheld at pack time) and stay bit-exact: accumulators up to ~7e7 and multipliers > 0.5."""
+    from convnet_quantization_b200 import _lib, ops
+    from convnet_quantization_b200.packing import PackedConv
+    from tests.conftest import qparams_to_numpy
+    order = ["in", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6"]
+    prev = order[order.index(name) - 1]
+    s, zp = qparams[prev]["out_scale"], qparams[prev]["out_zp"]
+    L = _stress_layer(name, qparams, huge=(mode == "huge_acc"))
+    if mode == "huge_acc":
+        # accumulators reach +-(9*cin*127*255): pick the output scale that maps that range onto ~+-100 LSB
+        k = 9 * L["w_int8"].shape[1]
+        L["out_scale"] = float(s) * float(L["w_scales"].max()) * (k * 127 * 255) / 100.0
+        L["out_zp"] = 128
+    else:
+        L["out_scale"] = float(L["out_scale"]) / 400.0    # mult = s_x*s_w/s_out > 0.5 -> not BOUNDED
+    pc = PackedConv(name, L, s, zp, "cuda")
+    if mode == "big_mult":
+        assert not (pc.c.rq.flags & _lib.RQ_BOUNDED)
+    else:
+        assert not (pc.c.rq.flags & _lib.RQ_ACC22)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(0, 256, (2, pc.img, pc.img, pc.cin), generator=g, dtype=torch.uint8)
+    x[0] = 255   # one saturated image: every accumulator of it is at the extreme
+    x[1, : pc.img // 2] = 0
+    Lnp = qparams_to_numpy({"l": L})["l"]
+    want = _want_conv(x.numpy(), s, zp, Lnp)
+    got = ops.conv2d_q(x.cuda(), pc, impl="tc")
+    torch.cuda.synchronize()
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert len(np.unique(want)) > 8  # not everything clamped
