@@ -82,7 +82,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 # ------------------------------------------------------------------ C structs (mirror include/b200q.h)
 class Requant(C.Structure):
     _fields_ = [("mult", C.c_void_p), ("bdiv", C.c_void_p), ("zp_out", C.c_int32), ("relu", C.c_int32),
-                ("flags", C.c_int32), ("reserved", C.c_int32)]
+                ("flags", C.c_int32), ("reserved", C.c_int32), ("mult_host", C.c_void_p), ("bdiv_host", C.c_void_p)]
 
 
 RQ_BOUNDED = 1  # B200Q_RQ_BOUNDED
@@ -91,12 +91,12 @@ RQ_ACC22 = 2    # B200Q_RQ_ACC22
 
 class Conv3x3(C.Structure):
     _fields_ = [("cin", C.c_int32), ("cout", C.c_int32), ("img", C.c_int32), ("zp_x", C.c_int32),
-                ("w", C.c_void_p), ("corr", C.c_void_p), ("rq", Requant)]
+                ("w", C.c_void_p), ("corr", C.c_void_p), ("corr_host", C.c_void_p), ("rq", Requant)]
 
 
 class Linear(C.Structure):
     _fields_ = [("k", C.c_int32), ("n", C.c_int32), ("zp_x", C.c_int32),
-                ("w", C.c_void_p), ("corr", C.c_void_p), ("rq", Requant)]
+                ("w", C.c_void_p), ("corr", C.c_void_p), ("corr_host", C.c_void_p), ("rq", Requant)]
 
 
 class StaticNet(C.Structure):

@@ -68,6 +68,11 @@ __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 // d = bytes {sat_u8(b), sat_u8(a), c[7:0], c[15:8]} (low to high): one I2IP.U8.S32.SAT
 __device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c) {
   uint32_t d;
@@ -111,6 +116,64 @@ __device__ __forceinline__ uint32_t requant4_magic(uint32_t a0, uint32_t a1, uin
 }
 // true when any accumulated range-check bit says |acc - corr| >= 2^22
 __device__ __forceinline__ bool requant_magic_out_of_range(uint32_t bad) { return (bad >> 23) != 0u; }
+
+// Variant for accumulators that were PRE-BIASED in TMEM with MAGIC_BITS (the epilogue re-arms each accumulator chunk with
+// tcgen05.st after reading it, and every MMA accumulates): v = raw + MAGIC_BITS reinterpreted as float IS f32(raw)+MAGIC_F
+// for |raw| < 2^22, so no integer instruction is needed at all.  k1 = -(MAGIC_F + corr) (exact for |corr| < 2^22) turns
+// it into f32(raw - corr) with one exact subtraction.  The rounding add is fma(t, 1.0, MAGIC_F): still one rounding of
+// t + MAGIC_F, but a packed instruction that ptxas cannot contract with the multiply before it.
+template <bool CHECK>
+__device__ __forceinline__ uint32_t requant4_prebiased(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, const float4 k1,
+                                                       const float4 bd, const float4 mu, int zp_sub, int lo,
+                                                       uint32_t& bad) {
+  if constexpr (CHECK) {
+    bad |= (v0 ^ 0x4B000000u);
+    bad |= (v1 ^ 0x4B000000u);
+    bad |= (v2 ^ 0x4B000000u);
+    bad |= (v3 ^ 0x4B000000u);
+  }
+  const uint64_t ones = f2_pack(1.0f, 1.0f), magic = f2_pack(MAGIC_F, MAGIC_F);
+  uint64_t t01 = f2_add(u2_pack(v0, v1), f2_pack(k1.x, k1.y));
+  uint64_t t23 = f2_add(u2_pack(v2, v3), f2_pack(k1.z, k1.w));
+  t01 = f2_mul(f2_add(t01, f2_pack(bd.x, bd.y)), f2_pack(mu.x, mu.y));
+  t23 = f2_mul(f2_add(t23, f2_pack(bd.z, bd.w)), f2_pack(mu.z, mu.w));
+  t01 = f2_fma(t01, ones, magic);
+  t23 = f2_fma(t23, ones, magic);
+  uint32_t r0, r1, r2, r3;
+  u2_unpack(t01, r0, r1);
+  u2_unpack(t23, r2, r3);
+  const int q0 = max((int)r0 + zp_sub, lo), q1 = max((int)r1 + zp_sub, lo);
+  const int q2 = max((int)r2 + zp_sub, lo), q3 = max((int)r3 + zp_sub, lo);
+  return pack_sat_u8(q1, q0, pack_sat_u8(q3, q2, 0u));
+}
+
+// 4*G channels of one pixel, pre-biased accumulators.  cm (int, MAGIC_BITS - corr) is only used by the exact fall-back.
+template <bool CHECK, int G>
+__device__ __forceinline__ void requant_chunk_prebiased(const uint32_t (&v)[4 * G], const int4* cm, const float4* k1,
+                                                        const float4* bd, const float4* mu, bool fast, int zp_out,
+                                                        int lo, uint32_t (&packed)[G]) {
+  const int zp_sub = zp_out - (int)MAGIC_BITS;
+  uint32_t bad = 0;
+  if (fast) {
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      packed[g] = requant4_prebiased<CHECK>(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], k1[g], bd[g], mu[g],
+                                            zp_sub, lo, bad);
+  }
+  if (!fast || (CHECK && __any_sync(0xffffffffu, requant_magic_out_of_range(bad)))) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int4 c = cm[g];
+      const float4 b = bd[g], m = mu[g];
+      // v = raw + MAGIC_BITS, cm = MAGIC_BITS - corr  ->  raw - corr = v + cm - 2*MAGIC_BITS (wrapping arithmetic)
+      packed[g] = requant_u8((int)(v[4 * g + 0] + (uint32_t)c.x - 2u * MAGIC_BITS), b.x, m.x, zp_out, lo) |
+                  (requant_u8((int)(v[4 * g + 1] + (uint32_t)c.y - 2u * MAGIC_BITS), b.y, m.y, zp_out, lo) << 8) |
+                  (requant_u8((int)(v[4 * g + 2] + (uint32_t)c.z - 2u * MAGIC_BITS), b.z, m.z, zp_out, lo) << 16) |
+                  (requant_u8((int)(v[4 * g + 3] + (uint32_t)c.w - 2u * MAGIC_BITS), b.w, m.w, zp_out, lo) << 24);
+    }
+  }
+}
+
 
 // 32 consecutive output channels of one pixel (one tcgen05.ld 32x32b.x32 worth): v -> 8 packed words.
 // cm: this pixel's border-class row of (MAGIC_BITS - corr), bd/mu: bdiv / mult, all at the chunk's first channel
@@ -292,6 +355,22 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// Fill 32 lanes x 8 consecutive 32-bit columns with one value (thread t writes lane base_lane + t).
+__device__ __forceinline__ void tmem_st_fill8(uint32_t taddr, uint32_t value) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(value)
+               : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns.
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 // 32 lanes x 32 consecutive 32-bit columns: thread t of the warp gets lane (base_lane + t), columns col..col+31.
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(

@@ -35,21 +35,25 @@ def requant_constants(s_x: float, w_scales: torch.Tensor, bias: torch.Tensor, s_
 
 
 def acc_bound(w_int8: torch.Tensor, zp_x: int) -> int:
-    """Largest |sum_k (x_k - zp_x) * w_k| any uint8 input can produce, over output channels."""
+    """Largest magnitude, over output channels and all uint8 inputs, of the raw accumulator ``sum x*w``, of the
+    zero-point-corrected one ``sum (x-zp_x)*w`` and of the correction ``zp_x*sum w`` itself."""
     w = w_int8.detach().cpu().to(torch.int64).reshape(w_int8.shape[0], -1)
     pos, neg = w.clamp(min=0).sum(1), (-w).clamp(min=0).sum(1)
-    hi = (255 - zp_x) * pos + zp_x * neg
-    lo = zp_x * pos + (255 - zp_x) * neg
-    return int(torch.maximum(hi, lo).max())
+    raw = 255 * torch.maximum(pos, neg)
+    acc = torch.maximum((255 - zp_x) * pos + zp_x * neg, zp_x * pos + (255 - zp_x) * neg)
+    corr = (zp_x * (pos - neg)).abs()
+    return int(torch.stack([raw, acc, corr]).max())
 
 
 def requant_flags(mult: torch.Tensor, bdiv: torch.Tensor, w_int8: torch.Tensor, zp_x: int) -> int:
-    """``B200Q_RQ_BOUNDED`` when every channel satisfies the bound under which the conversion-free requantisation of
+    """``B200Q_RQ_BOUNDED`` when every channel satisfies the bounds under which the conversion-free requantisation of
     the tensor-core epilogue is exact, ``B200Q_RQ_ACC22`` when no input can push an accumulator past 2^22
     (``include/b200q.h``)."""
     flags = 0
-    if bool((mult >= 0).all() and (mult <= 0.5).all() and (bdiv.abs() <= 2.0 ** 21).all()
-            and torch.isfinite(mult).all() and torch.isfinite(bdiv).all()):
+    w = w_int8.detach().cpu().to(torch.int64).reshape(w_int8.shape[0], -1)
+    corr_ok = bool(((zp_x * w.sum(1)).abs() < 2 ** 22).all())
+    if corr_ok and bool((mult >= 0).all() and (mult <= 0.5).all() and (bdiv.abs() <= 2.0 ** 21).all()
+                        and torch.isfinite(mult).all() and torch.isfinite(bdiv).all()):
         flags |= _lib.RQ_BOUNDED
     if acc_bound(w_int8, zp_x) < 2 ** 22:
         flags |= _lib.RQ_ACC22
@@ -80,11 +84,16 @@ class PackedConv:
         self.name, self.cin, self.cout, self.img = name, cin_p, cout, img
         self.zp_x, self.zp_out, self.s_out = int(zp_x), int(layer["out_zp"]), float(layer["out_scale"])
         self.w = wk.contiguous().to(device)
-        self.corr = conv_border_corr(w, zp_x).to(device)
+        # host mirrors stay alive with the object: the C struct points at them (kernel-parameter constants)
+        self.corr_host = conv_border_corr(w, zp_x)
+        self.mult_host, self.bdiv_host = mult, bdiv
+        self.corr = self.corr_host.to(device)
         self.mult, self.bdiv = mult.to(device), bdiv.to(device)
         self.c = _lib.Conv3x3(cin_p, cout, img, self.zp_x, self.w.data_ptr(), self.corr.data_ptr(),
+                              self.corr_host.data_ptr(),
                               _lib.Requant(self.mult.data_ptr(), self.bdiv.data_ptr(), self.zp_out, int(relu),
-                                           requant_flags(mult, bdiv, w, zp_x), 0))
+                                           requant_flags(mult, bdiv, w, zp_x), 0, self.mult_host.data_ptr(),
+                                           self.bdiv_host.data_ptr()))
 
     def ptr(self):
         return C.byref(self.c)
@@ -101,11 +110,14 @@ class PackedLinear:
         self.name, self.k, self.n = name, k, n
         self.zp_x, self.zp_out, self.s_out = int(zp_x), int(layer["out_zp"]), float(layer["out_scale"])
         self.w = w.contiguous().to(device)
-        self.corr = (w.to(torch.int64).sum(dim=1) * int(zp_x)).to(torch.int32).contiguous().to(device)
+        self.corr_host = (w.to(torch.int64).sum(dim=1) * int(zp_x)).to(torch.int32).contiguous()
+        self.mult_host, self.bdiv_host = mult, bdiv
+        self.corr = self.corr_host.to(device)
         self.mult, self.bdiv = mult.to(device), bdiv.to(device)
-        self.c = _lib.Linear(k, n, self.zp_x, self.w.data_ptr(), self.corr.data_ptr(),
+        self.c = _lib.Linear(k, n, self.zp_x, self.w.data_ptr(), self.corr.data_ptr(), self.corr_host.data_ptr(),
                              _lib.Requant(self.mult.data_ptr(), self.bdiv.data_ptr(), self.zp_out, int(relu),
-                                          requant_flags(mult, bdiv, w, zp_x), 0))
+                                          requant_flags(mult, bdiv, w, zp_x), 0, self.mult_host.data_ptr(),
+                                          self.bdiv_host.data_ptr()))
 
     def ptr(self):
         return C.byref(self.c)

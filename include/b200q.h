@@ -48,13 +48,18 @@ typedef struct b200q_requant {
   int32_t relu;           /* 1: clamp low at zp_out (aten::relu on quint8 == max(q, zp)) */
   int32_t flags;          /* B200Q_RQ_* */
   int32_t reserved;
+  /* Optional HOST copies of mult / bdiv (same contents).  When present (together with corr_host of the layer) the
+   * kernels that take their per-channel constants as kernel parameters are eligible; NULL selects the kernels that
+   * stage the device tables through shared memory. */
+  const float* mult_host;
+  const float* bdiv_host;
 } b200q_requant;
-/* Caller guarantees 0 <= mult[c] <= 0.5 and |bdiv[c]| <= 2^21 for every channel.  The tensor-core kernels then use a
+/* Caller guarantees 0 <= mult[c] <= 0.5, |bdiv[c]| <= 2^21 and |corr| < 2^22 for every channel.  The tensor-core kernels then use a
  * conversion-free formulation of the same arithmetic (bit-identical; accumulators outside +-2^22 are detected at run
  * time and take the I2F/F2I form).  Without the flag the I2F/F2I form is always used. */
 #define B200Q_RQ_BOUNDED 1
-/* Caller guarantees |acc - corr| < 2^22 for every possible uint8 input (a bound on the layer's weights, see
- * packing.acc_bound): lets the N=64 kernels skip the per-element run-time range test. */
+/* Caller guarantees |sum x*w| < 2^22 and |sum (x-zp_x)*w| < 2^22 for every possible uint8 input (a bound on the
+ * layer's weights, see packing.acc_bound): lets the N=64 kernels skip the per-element run-time range test. */
 #define B200Q_RQ_ACC22 2
 
 /* 3x3 / stride 1 / pad 1 quantized convolution layer, packed.
@@ -66,6 +71,7 @@ typedef struct b200q_conv3x3 {
   int32_t zp_x;               /* input activation zero-point */
   const int8_t*  w;           /* [cout][3][3][cin_padded] */
   const int32_t* corr;        /* [9][cout]: zp_x * sum of w over the taps valid for border class (3*rowclass+colclass) */
+  const int32_t* corr_host;   /* optional HOST copy of corr (see b200q_requant.mult_host) */
   b200q_requant rq;
 } b200q_conv3x3;
 
@@ -75,6 +81,7 @@ typedef struct b200q_linear {
   int32_t zp_x;
   const int8_t*  w;           /* [n][k] */
   const int32_t* corr;        /* [n]: zp_x * sum_k w[n][k] */
+  const int32_t* corr_host;   /* optional HOST copy of corr */
   b200q_requant rq;
 } b200q_linear;
 

@@ -23,8 +23,16 @@ elif a.layer == "fc1":
     x = torch.randint(0, 256, (a.batch, 4096), dtype=torch.uint8, device="cuda", generator=g)
     fn = lambda: ops.linear_q(x, packed.fc1)
 else:
-    pc = packed.convs[int(a.layer[-1]) - 1]
-    x = torch.randint(0, 256, (a.batch, pc.img, pc.img, pc.cin), dtype=torch.uint8, device="cuda", generator=g)
+    # realistic activations: the layer's true input from a forward of the whole net (taps), tiled up to the batch
+    from convnet_quantization_b200.engine import StaticEngine
+    idx = int(a.layer[-1])
+    pc = packed.convs[idx - 1]
+    src = {2: "conv1", 3: "pool1", 4: "conv3", 5: "pool2", 6: "conv5"}[idx]
+    eng = StaticEngine(ptq.calibrate_static(net.eval(), synth.calibration_batches()), "cuda")
+    nb = min(a.batch, 1024)
+    _, taps = eng.forward(synth.images_f32(nb, seed=5).cuda(), taps=True)
+    x = taps[src].repeat((a.batch + nb - 1) // nb, 1, 1, 1)[:a.batch].contiguous()
+    del eng, taps
     fn = lambda: ops.conv2d_q(x, pc, pool2x2=a.pool)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 fn(); torch.cuda.synchronize()

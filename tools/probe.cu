@@ -44,6 +44,65 @@ __global__ void __launch_bounds__(128, 1) mma_probe(int iters, long long* cycles
   if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
 }
 
+// Lean issue loop: descriptors precomputed, 8 MMAs per iteration back to back (no per-MMA integer work).
+template <int N, int KC>
+__global__ void __launch_bounds__(128, 1) mma_probe_lean(int iters, long long* cycles, int shift_rows = 0) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a = smem;
+  uint8_t* b = smem + 4 * 128 * KC;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  for (int i = threadIdx.x; i < (4 * 128 * KC + N * KC) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x01010101u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (threadIdx.x < 32) {
+    const bool leader = elect_one() != 0;
+    constexpr uint32_t idesc = make_idesc_i8(128, N);
+    const uint64_t da0 = make_kmajor_desc<KC>(smem_u32(a) + shift_rows * KC, 8 * KC);
+    const uint64_t db0 = make_kmajor_desc<KC>(smem_u32(b), 8 * KC);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; i += 8) {
+      if (leader) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          tc_mma_i8(tmem + (u & 1) * N, da0 + (uint64_t)(((u & 3) * 128 * KC + (u & 1) * 32) >> 4), db0 + (uint64_t)(((u & 1) * 32) >> 4), idesc, 1u);
+      }
+      __syncwarp();
+    }
+    if (leader) { tc_commit(&bar); }
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0 && threadIdx.x == 0) cycles[0] = t1 - t0;
+  }
+  tc_fence_before(); __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
+template <int N, int KC>
+void run_lean(long long* d_cycles) {
+  const int iters = 8192;
+  const int smem = 4 * 128 * KC + N * KC + 2048;
+  cudaFuncSetAttribute(mma_probe_lean<N, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int sh = 1; sh <= 8; ++sh) {
+    mma_probe_lean<N, KC><<<148, 128, smem>>>(iters, d_cycles, sh);
+    cudaDeviceSynchronize();
+    long long cs = 0;
+    cudaMemcpy(&cs, d_cycles, 8, cudaMemcpyDeviceToHost);
+    printf("LEAN N=%3d KC=%3d A shifted %d rows: %.1f cyc/MMA\n", N, KC, sh, (double)cs / iters);
+  }
+  mma_probe_lean<N, KC><<<148, 128, smem>>>(iters, d_cycles, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long c = 0;
+  cudaMemcpy(&c, d_cycles, 8, cudaMemcpyDeviceToHost);
+  const double per = (double)c / iters;
+  printf("LEAN mma i8 M=128 N=%3d KC=%3d: %.1f cyc/MMA (%.0f MAC/cyc/SM, smem operand %.0f B/cyc) [%s]\n", N, KC, per, 128.0 * N * 32 / per,
+         (128.0 * 32 + N * 32.0) / per, cudaGetErrorString(e));
+}
+
 // TMEM load rate: W warps each load their lane quarter, 32 columns at a time, `iters` times.
 __global__ void __launch_bounds__(512, 1) ldtm_probe(int iters, long long* cycles, uint32_t* sink) {
   __shared__ uint32_t tmem_base_s;
@@ -149,6 +208,7 @@ void run_mma(long long* d_cycles) {
 int main() {
   long long* d_cycles; int* d_sink;
   cudaMalloc(&d_cycles, 64); cudaMalloc(&d_sink, 64);
+  run_lean<16, 64>(d_cycles); run_lean<32, 64>(d_cycles); run_lean<64, 64>(d_cycles); run_lean<128, 64>(d_cycles); run_lean<64, 128>(d_cycles); run_lean<128, 128>(d_cycles); run_lean<256, 128>(d_cycles); run_lean<64, 32>(d_cycles);
   run_mma<64, 64>(d_cycles); run_mma<128, 64>(d_cycles); run_mma<64, 128>(d_cycles); run_mma<128, 128>(d_cycles); run_mma<256, 128>(d_cycles);
   run_mma<32, 64>(d_cycles); run_mma<16, 64>(d_cycles);
   for (int threads : {128, 256, 512}) {
