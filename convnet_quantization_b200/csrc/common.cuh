@@ -20,6 +20,9 @@ int launched(const char* what);  // after every <<<>>>: bumps b200q_launch_count
 #define B200Q_REQUIRE(cond, ...) do { if (!(cond)) { ::b200q::set_error(__VA_ARGS__); return B200Q_ERR_INVALID_ARG; } } while (0)
 int num_sms();
 // conv_halo.cu: halo-resident kernel for the cin=64 layers; returns 1 when the geometry is not covered
+// conv1_tc.cu: tensor-core first layer (fused quantize); returns 1 when the layer cannot take that path
+int conv1_tc_dispatch(const float* x, uint8_t* y, int64_t b, float inv_scale, const b200q_conv3x3* L, cudaStream_t s,
+                      int* rc);
 int conv3x3_halo_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, bool pool, cudaStream_t s,
                           int* rc);
 

@@ -264,6 +264,16 @@ static int conv_first_impl(const void* x, uint8_t* y, int64_t b, const b200q_con
                 L->img);
   B200Q_REQUIRE((uintptr_t)y % 16 == 0 && (uintptr_t)x % 4 == 0, "conv3x3_first: misaligned buffers");
   if (b == 0) return 0;
+  if (fused) {  // tensor-core version unless B200Q_NO_CONV1_TC=1 (A-B testing) or the layer lacks host mirrors
+    static int no_tc = -1;
+    if (no_tc < 0) {
+      const char* e = getenv("B200Q_NO_CONV1_TC");
+      no_tc = (e && e[0] == '1') ? 1 : 0;
+    }
+    int trc = 0;
+    if (!no_tc && conv1_tc_dispatch(reinterpret_cast<const float*>(x), y, b, inv_scale, L, (cudaStream_t)stream, &trc) == 0)
+      return trc;
+  }
   const unsigned grid = (unsigned)(b * (L->img / C1_ROWS));
   const uint32_t* ww = reinterpret_cast<const uint32_t*>(L->w);
   if (fused)
