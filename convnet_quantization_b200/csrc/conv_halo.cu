@@ -1,4 +1,5 @@
-// Halo-resident tcgen05 implicit-GEMM 3x3 convolution for the 64-input-channel layers (conv2, conv3).
+// Halo-resident tcgen05 implicit-GEMM 3x3 convolution for the layers whose weights fit in shared memory next to a
+// double-buffered band of input images (conv2, conv3: cin=64; conv4: cin=128).
 //
 // The shifted-TMA formulation (igemm_tc.cu) re-reads every activation tile from L2 nine times (once per filter tap);
 // on B200 the L2->SM path sustains about what HBM does, so those layers were L2-bound at ~4x their MMA time.  Here
@@ -43,9 +44,9 @@ constexpr int HALO_THREADS = 64 + 32 * HALO_EPI_WARPS;
 constexpr int HALO_LOAD_WARP = HALO_EPI_WARPS, HALO_MMA_WARP = HALO_EPI_WARPS + 1;
 constexpr int HALO_SLOTS = 4;  // TMEM accumulator slots
 
-template <int IMG, int COUT, int NBI, bool POOL>
+template <int IMG, int CIN_, int COUT, int NBI, bool POOL>
 struct HaloCfg {
-  static constexpr int CIN = 64;                 // bytes per pixel row == swizzle span (SWIZZLE_64B)
+  static constexpr int CIN = CIN_;               // bytes per pixel row == swizzle span (SWIZZLE_64B / SWIZZLE_128B)
   static constexpr int P = IMG + 1;              // pitch of the padded pixel sequence
   static constexpr int POS_PER_IMG = (IMG + 1) * P;
   static constexpr int BOX_POS = NBI * POS_PER_IMG;
@@ -61,6 +62,7 @@ struct HaloCfg {
   static constexpr int COLS_PER_WARP = COUT / (HALO_EPI_WARPS / 4);
   static constexpr int UNITS_PER_WARP = COLS_PER_WARP / 16;   // the epilogue works in units of 16 channels
   static_assert(COUT == 64 || COUT == 128, "COUT");
+  static_assert(CIN == 64 || CIN == 128, "CIN");
   static_assert(IMG % TILE_ROWS == 0 && IMG % TILE_COLS == 0, "tiles must cover the image exactly");
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
@@ -94,11 +96,11 @@ __device__ __forceinline__ uint32_t max2_u8x4(uint32_t a, uint32_t b) {
   return __byte_perm(e, o, 0x6240);
 }
 
-template <int IMG, int COUT, int NBI, bool POOL, bool CHECK>
+template <int IMG, int CIN, int COUT, int NBI, bool POOL, bool CHECK>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ HaloConsts<COUT> consts,
                  const HaloArgs args) {
-  using C = HaloCfg<IMG, COUT, NBI, POOL>;
+  using C = HaloCfg<IMG, CIN, COUT, NBI, POOL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_smem = smem;                                  // 2 x A_BYTES
@@ -174,9 +176,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       for (int tap = 0; tap < 9; ++tap)
         tma_load_2d(w_smem + tap * C::W_TAP_BYTES, &map_w, w_bar, tap * C::CIN, 0);
     }
-    // 16-byte chunk g of an image: global offset g*16 (linear), pixel g/4 = (h, w), part g%4;
-    // shared: position (h+1)*P + (w+1) of the image's slot, chunk slot part ^ ((pos >> 1) & 3)  (SWIZZLE_64B on
-    // absolute addresses; the buffers are 1 KiB aligned)
+    // 16-byte chunk g of an image: global offset g*16 (linear), pixel g/(CIN/16) = (h, w), part g%(CIN/16);
+    // shared: position (h+1)*P + (w+1) of the image's slot, chunk slot part ^ swz(pos): address bits [7,9) (64-byte
+    // rows) or [7,10) (128-byte rows) XORed into bits [4,..) - the hardware swizzle on absolute addresses (the buffers
+    // are 1 KiB aligned)
     constexpr int CHUNKS_PER_IMG = IMG * IMG * (C::CIN / 16);
     int it = 0;
     for (int band = blockIdx.x; band < args.num_bands; band += gridDim.x, ++it) {
@@ -189,9 +192,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
         const uint8_t* src = args.x + img * (int64_t)(IMG * IMG * C::CIN);
 #pragma unroll 8
         for (int g = lane; g < CHUNKS_PER_IMG; g += 32) {
-          const int px = g >> 2, part = g & 3;
+          const int px = g / (C::CIN / 16), part = g % (C::CIN / 16);
           const int pos = bi * C::POS_PER_IMG + (px / IMG + 1) * C::P + (px % IMG) + 1;
-          const uint32_t dst = a_buf + pos * C::CIN + ((part ^ ((pos >> 1) & 3)) << 4);
+          const int swz = (C::CIN == 64) ? ((pos >> 1) & 3) : (pos & 7);
+          const uint32_t dst = a_buf + pos * C::CIN + ((part ^ swz) << 4);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + g * 16) : "memory");
         }
       }
@@ -320,13 +324,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   }
 }
 
-template <int IMG, int COUT, int NBI, bool POOL, bool CHECK = true>
+template <int IMG, int CIN, int COUT, int NBI, bool POOL, bool CHECK = true>
 static int launch_halo(const uint8_t* x, uint8_t* y, int64_t n_img, const b200q_conv3x3* L, cudaStream_t stream) {
-  using C = HaloCfg<IMG, COUT, NBI, POOL>;
+  using C = HaloCfg<IMG, CIN, COUT, NBI, POOL>;
   const b200q_requant& rq = L->rq;
   if constexpr (CHECK && COUT == 64) {
     if ((rq.flags & B200Q_RQ_BOUNDED) && (rq.flags & B200Q_RQ_ACC22))
-      return launch_halo<IMG, COUT, NBI, POOL, false>(x, y, n_img, L, stream);
+      return launch_halo<IMG, CIN, COUT, NBI, POOL, false>(x, y, n_img, L, stream);
   }
   CUtensorMap map_w;
   {
@@ -345,7 +349,7 @@ static int launch_halo(const uint8_t* x, uint8_t* y, int64_t n_img, const b200q_
     consts.bdiv[c] = rq.bdiv_host[c];
     consts.mult[c] = rq.mult_host[c];
   }
-  auto kernel = conv_halo_kernel<IMG, COUT, NBI, POOL, CHECK>;
+  auto kernel = conv_halo_kernel<IMG, CIN, COUT, NBI, POOL, CHECK>;
   static bool attr_set = false;
   if (!attr_set) {
     B200Q_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -368,13 +372,17 @@ static int launch_halo(const uint8_t* x, uint8_t* y, int64_t n_img, const b200q_
 int conv3x3_halo_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, bool pool, cudaStream_t s,
                           int* rc) {
   // needs the host mirrors of the per-channel constants (they become kernel parameters)
-  if (L->cin != 64 || !L->corr_host || !L->rq.mult_host || !L->rq.bdiv_host) return 1;
-  if (L->img == 32 && L->cout == 64) {
-    *rc = pool ? launch_halo<32, 64, 1, true>(x, y, b, L, s) : launch_halo<32, 64, 1, false>(x, y, b, L, s);
+  if (!L->corr_host || !L->rq.mult_host || !L->rq.bdiv_host) return 1;
+  if (L->img == 32 && L->cin == 64 && L->cout == 64) {
+    *rc = pool ? launch_halo<32, 64, 64, 1, true>(x, y, b, L, s) : launch_halo<32, 64, 64, 1, false>(x, y, b, L, s);
     return 0;
   }
-  if (L->img == 16 && L->cout == 128 && !pool) {
-    *rc = launch_halo<16, 128, 3, false>(x, y, b, L, s);
+  if (L->img == 16 && L->cin == 64 && L->cout == 128 && !pool) {
+    *rc = launch_halo<16, 64, 128, 3, false>(x, y, b, L, s);
+    return 0;
+  }
+  if (L->img == 16 && L->cin == 128 && L->cout == 128) {  // weights (144 KiB) + two single-image bands
+    *rc = pool ? launch_halo<16, 128, 128, 1, true>(x, y, b, L, s) : launch_halo<16, 128, 128, 1, false>(x, y, b, L, s);
     return 0;
   }
   return 1;
