@@ -29,16 +29,20 @@ class StaticEngine:
         self.qparams = qparams
         with torch.cuda.device(self.device):
             self.packed = PackedStaticNet(qparams, self.device)
-        self._ws = None
+        self._ws = {}  # CUDA stream handle -> workspace (forwards on different streams must not share one)
 
     def _workspace(self, b: int) -> torch.Tensor:
         need = int(self.lib.b200q_static_workspace_bytes(b))
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._ws
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor, taps: bool = False):
+    def forward(self, x: torch.Tensor, taps: bool = False, out: torch.Tensor | None = None):
+        """``out`` (optional): preallocated fp32 ``[B,10]`` CUDA tensor to receive the logits."""
         if not x.is_cuda:
             raise _lib.B200QError("StaticEngine.forward expects a CUDA tensor")
         x = x.contiguous().float()
@@ -46,7 +50,7 @@ class StaticEngine:
             raise _lib.B200QError(f"expected [B,3,32,32] input, got {tuple(x.shape)}")
         b = x.shape[0]
         with torch.cuda.device(self.device):
-            logits = torch.empty((b, 10), dtype=torch.float32, device=self.device)
+            logits = out if out is not None else torch.empty((b, 10), dtype=torch.float32, device=self.device)
             if b == 0:
                 return (logits, {}) if taps else logits
             ws = self._workspace(b)

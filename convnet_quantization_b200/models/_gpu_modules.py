@@ -66,19 +66,62 @@ class _GpuResident(nn.Module):
 
 
 class B200StaticQuantizedNet(_GpuResident):
-    """True static-PTQ int8 ``SimpleConvNet`` (all eight layers int8, fbgemm-exact requantisation) on a B200."""
+    """True static-PTQ int8 ``SimpleConvNet`` (all eight layers int8, fbgemm-exact requantisation) on a B200.
+
+    Host inputs (what ``utils/model_evaluator.py`` hands over, and ``utils/inference_benchmark.py`` with
+    ``device='cpu'``) are processed in chunks on two CUDA streams, so the host->device copy of chunk i+1 overlaps
+    the kernels of chunk i; logits come back through a pinned staging buffer."""
+
+    HOST_CHUNK = 4096  # images per pipelined chunk (48 MiB of fp32 input)
 
     def __init__(self, qparams: dict, device=None):
         super().__init__(device)
         self.qparams = qparams
         self.engine = StaticEngine(qparams, self.engine_device)
+        self._pipe = None
 
     def _rehome(self, device):
         self.engine = StaticEngine(self.qparams, device)
         self.engine_device = device
+        self._pipe = None
+
+    def _pipeline(self):
+        if self._pipe is None:
+            dev = self.engine_device
+            self._pipe = {
+                "streams": [torch.cuda.Stream(dev), torch.cuda.Stream(dev)],
+                "x": [torch.empty((self.HOST_CHUNK, 3, 32, 32), dtype=torch.float32, device=dev) for _ in range(2)],
+                "y": [torch.empty((self.HOST_CHUNK, 10), dtype=torch.float32, device=dev) for _ in range(2)],
+                "out": None,
+            }
+        return self._pipe
+
+    def _forward_host(self, x: torch.Tensor) -> torch.Tensor:
+        b = x.shape[0]
+        x = x.contiguous()
+        pipe = self._pipeline()
+        if pipe["out"] is None or pipe["out"].shape[0] < b:
+            pipe["out"] = torch.empty((max(b, self.HOST_CHUNK), 10), dtype=torch.float32).pin_memory()
+        out = pipe["out"][:b]
+        cur = torch.cuda.current_stream(self.engine_device)
+        for s in pipe["streams"]:
+            s.wait_stream(cur)
+        for i, lo in enumerate(range(0, b, self.HOST_CHUNK)):
+            n = min(self.HOST_CHUNK, b - lo)
+            k = i & 1
+            with torch.cuda.stream(pipe["streams"][k]):  # per-stream buffers: reuse is ordered by the stream itself
+                xin, yout = pipe["x"][k][:n], pipe["y"][k][:n]
+                xin.copy_(x[lo:lo + n], non_blocking=True)
+                self.engine.forward(xin, out=yout)
+                out[lo:lo + n].copy_(yout, non_blocking=True)
+        for s in pipe["streams"]:
+            s.synchronize()
+        return out.clone()  # the pinned staging buffer is reused by the next call
 
     @torch.no_grad()
     def forward(self, x):
+        if not x.is_cuda and x.dim() == 4 and x.shape[0] > 0:
+            return self._forward_host(x.float())
         return self._run(x, self.engine.forward)
 
     @torch.no_grad()
@@ -106,16 +149,24 @@ class B200DynamicQuantizedNet(_GpuResident):
     this is the tolerance path, not the product) and both linears run ``b200q_linear_dynamic`` (device-side min/max ->
     qparams -> quantize -> int8 GEMM -> fp32)."""
 
-    def __init__(self, fused_fp32: nn.Module, fc_weights: dict, device=None):
+    def __init__(self, fused_fp32: nn.Module, fc_weights: dict, device=None, bn_after_fc1: nn.Module | None = None):
+        """``bn_after_fc1``: eval-mode BatchNorm1d applied to fc1's output when fc1 was quantised WITHOUT the
+        batch-norm folded in (``StaticPTQModel`` as written quantises the unfused net: fc1 -> bn7 -> relu)."""
         super().__init__(device)
         self._fused_cpu = fused_fp32
         self._fc_cpu = fc_weights  # name -> (w_int8, w_scale, bias)
+        self._bn_cpu = None
+        if bn_after_fc1 is not None:
+            bn = bn_after_fc1
+            scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float()
+            self._bn_cpu = (scale, (bn.bias - bn.running_mean * scale).detach().float())
         self._build(self.engine_device)
 
     def _build(self, device):
         self.convs = [(getattr(self._fused_cpu, f"conv{i}").weight.detach().to(device),
                        getattr(self._fused_cpu, f"conv{i}").bias.detach().to(device)) for i in range(1, 7)]
         self.fc = {n: ops.DynamicLinearWeights(w, s, b, device) for n, (w, s, b) in self._fc_cpu.items()}
+        self.bn = None if self._bn_cpu is None else tuple(t.to(device) for t in self._bn_cpu)
 
     def _rehome(self, device):
         self._build(device)
@@ -133,7 +184,10 @@ class B200DynamicQuantizedNet(_GpuResident):
 
     def _forward_dev(self, x):
         x = self.features(x)
-        x = ops.linear_dynamic(x, self.fc["fc1"], relu=True)
+        if self.bn is None:
+            x = ops.linear_dynamic(x, self.fc["fc1"], relu=True)
+        else:  # unfused fc1: batch-norm, then ReLU, in fp32 (tolerance path)
+            x = F.relu(ops.linear_dynamic(x, self.fc["fc1"], relu=False) * self.bn[0] + self.bn[1]).contiguous()
         return ops.linear_dynamic(x, self.fc["fc2"], relu=False)
 
     @torch.no_grad()

@@ -46,8 +46,10 @@ class StaticPTQModel:
         if self.mode == "as_written":
             from .dynamic_ptq_model import dynamic_linear_weights
             net = self.fp32_model.cpu()
+            # convolutions: BN folded for execution only (numerically the unfused eval-mode net); fc1 is quantised from
+            # the UNFUSED weights as the reference does, so its batch-norm runs after the dynamic linear
             self.quantized_model = B200DynamicQuantizedNet(ptq.fold_identity(net), dynamic_linear_weights(net, fused=False),
-                                                           self.device)
+                                                           self.device, bn_after_fc1=net.bn7)
             return self.quantized_model
         batches = (synth.calibration_batches() if calibration_data_loader is None
                    else _calibration_tensors(calibration_data_loader))
