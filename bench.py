@@ -276,12 +276,8 @@ def run_ours(args):
     assert torch.equal(out_host, logits.cpu()), "e2e logits differ from the device-resident run"
 
     # ---- correct-count: the only collective, off the hot path (one NCCL all-reduce of 3 int64)
-    top5 = logits.topk(5, dim=1).indices
-    hit = top5.eq(labels.view(-1, 1))
-    counts = torch.stack([hit[:, 0].sum(), hit.sum(), torch.tensor(B, device=dev)]).to(torch.int64)
-    if world > 1:
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    counts = [int(v) for v in counts.tolist()]
+    from convnet_quantization_b200 import sharding
+    counts = [int(v) for v in sharding.allreduce_counts(sharding.topk_counts(logits, labels)).tolist()]
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
