@@ -7,8 +7,9 @@
 // requantised channels per pixel) and by the 77.8 KB/image it moves through HBM.  What the CUDA-core version
 // (simt.cu) spent on 576 dp4a + 128 conversion-pipe instructions per pixel is gone.
 //
-// Roles (672 threads): warps 0..15 epilogue (same scheme as conv_halo.cu: 8x16-pixel block tiles, four TMEM slots,
-// pre-biased accumulators, constants as kernel parameters), warps 16..19 producers, warp 20 MMA issuer.
+// Roles (416 threads): warps 0..7 epilogue (epilogue16.cuh, same scheme as conv_halo.cu: 8x16-pixel block tiles, four
+// TMEM slots, pre-biased accumulators, two sets of four warps taking alternate tiles), warps 8..11 producers, warp 12
+// MMA issuer.  13 warps leave 128 registers per thread, which the register-resident epilogue constants need.
 // Producers, per image: (1) quantise the fp32 planes (exact aten arithmetic, without the conversion pipe) into a
 // padded 34x34 image of {c0,c1,c2,zp} words whose border holds the zero-point; (2) gather the im2col rows
 // [pixel][tap*3+ch] (27 bytes + 5 zero bytes) with byte permutes and store them tile-major in the 32-byte-swizzled
@@ -17,10 +18,12 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "epilogue16.cuh"
 
 namespace b200q {
 
-constexpr int C1_EPI_WARPS = 16, C1_PROD_WARPS = 4;
+constexpr int C1_EPI_WARPS = 8, C1_PROD_WARPS = 4;
+constexpr int C1_SETS = C1_EPI_WARPS / 4;
 constexpr int C1_PROD_WARP0 = C1_EPI_WARPS, C1_MMA_WARP = C1_EPI_WARPS + C1_PROD_WARPS;
 constexpr int C1_THREADS = 32 * (C1_EPI_WARPS + C1_PROD_WARPS + 1);
 constexpr int C1_SLOTS = 4;
@@ -82,7 +85,7 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
     }
     for (int i = 0; i < C1_SLOTS; ++i) {
       mbar_init(tmem_full_bar + i, 1);
-      mbar_init(tmem_empty_bar + i, C1_EPI_WARPS);
+      mbar_init(tmem_empty_bar + i, 4);  // the four warps of the set that drains this slot
     }
     fence_barrier_init();
   }
@@ -97,17 +100,19 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
       const int r = i / C1_QP, c = i % C1_QP;
       if (r == 0 || r == C1_QP - 1 || c == 0 || c == C1_QP - 1) q_img[i] = zp4;
     }
-    // weights [64][9][4] -> B operand [64][k = tap*3 + ch] (32-byte rows, SWIZZLE_32B), zero for k >= 27
+    // weights [64][9][4] -> B operand [64][k = tap*3 + ch] (32-byte rows, SWIZZLE_32B), zero for k >= 27; row nr holds
+    // output channel epi16_channel_of_column(nr) (the epilogue's thread <-> channel assignment)
     for (int i = t; i < C1_COUT * (C1_KB / 4); i += 32 * C1_EPI_WARPS) {
-      const int n = i / (C1_KB / 4), wd = i % (C1_KB / 4);
+      const int nr = i / (C1_KB / 4), wd = i % (C1_KB / 4);
+      const int n = epi16_channel_of_column(nr);
       uint32_t word = 0;
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const int k = wd * 4 + b;
         if (k < 27) word |= (uint32_t)(uint8_t)__ldg(args.w + (n * 9 + k / 3) * 4 + k % 3) << (8 * b);
       }
-      const int chunk = (wd >> 2) ^ ((n >> 2) & 1);
-      *reinterpret_cast<uint32_t*>(b_smem + n * C1_KB + chunk * 16 + (wd & 3) * 4) = word;
+      const int chunk = (wd >> 2) ^ ((nr >> 2) & 1);
+      *reinterpret_cast<uint32_t*>(b_smem + nr * C1_KB + chunk * 16 + (wd & 3) * 4) = word;
     }
     fence_proxy_async_smem();
   }
@@ -115,12 +120,10 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
-  if (warp < C1_EPI_WARPS) {  // pre-bias every accumulator slot (see requant4_prebiased)
-    const uint32_t base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 16;
-    for (int slot = 0; slot < C1_SLOTS; ++slot) {
-      tmem_st_fill8(base + slot * C1_COUT, MAGIC_BITS);
-      tmem_st_fill8(base + slot * C1_COUT + 8, MAGIC_BITS);
-    }
+  if (warp < 4) {  // pre-bias every accumulator slot (see requant4_prebiased)
+    const uint32_t base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int slot = 0; slot < C1_SLOTS; ++slot)
+      for (int c = 0; c < C1_COUT; c += 8) tmem_st_fill8(base + slot * C1_COUT + c, MAGIC_BITS);
     tmem_st_wait();
   }
   tc_fence_before();
@@ -212,44 +215,27 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
   } else {
     // ================================================================== epilogue warps (independent of each other)
     const int quarter = warp & 3;
-    const int part = warp >> 2;               // 16-channel slice
-    const int g_row = quarter * 4 + (lane >> 3), g_col = lane & 7;
+    const int set = warp >> 2;                 // takes the tiles with acc_it % C1_SETS == set
+    const int j = lane >> 2;                   // column of the 8-column block
+    const int ch0 = 16 * (lane & 3);
     const bool fast = args.bounded != 0;
-    int acc_it = 0;
+    Epi16Regs K;
+    epi16_init(consts, ch0, K);
+    static_assert(C1_TILES % C1_SETS == 0 && C1_SLOTS % C1_SETS == 0, "sets");
     for (int it = 0; it < my_imgs; ++it) {
       const int64_t img = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
-      for (int t = 0; t < C1_TILES; ++t, ++acc_it) {
+      for (int t = set; t < C1_TILES; t += C1_SETS) {
+        const int acc_it = it * C1_TILES + t;
         const uint32_t slot = acc_it % C1_SLOTS;
-        const int r = (t >> 2) * 16 + g_row, c = (t & 3) * 8 + g_col;
-        uint8_t* out_px = args.y + ((img * C1_IMG + r) * C1_IMG + c) * (int64_t)C1_COUT;
+        const int r0 = (t >> 2) * 16 + 4 * quarter, c = (t & 3) * 8 + j;
+        uint8_t* out = args.y + ((img * C1_IMG + r0) * C1_IMG + c) * (int64_t)C1_COUT + ch0;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * C1_COUT;
+        auto release = [&]() {
+          if (lane == 0) mbar_arrive(tmem_empty_bar + slot);
+        };
         mbar_wait(tmem_full_bar + slot, (acc_it / C1_SLOTS) & 1);
         tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * C1_COUT;
-        auto do_part = [&](auto part_tag) {
-          constexpr int c0 = decltype(part_tag)::value * 16;
-          uint32_t v[16];
-          tmem_ld_32x16(t_row + c0, v);
-          tmem_ld_wait();
-          tmem_st_fill8(t_row + c0, MAGIC_BITS);  // re-arm for the tile that reuses this slot
-          tmem_st_fill8(t_row + c0 + 8, MAGIC_BITS);
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty_bar + slot);
-          uint32_t packed[4];
-          requant_chunk_prebiased<CHECK, 4>(v, reinterpret_cast<const int4*>(consts.cm + c0),
-                                            reinterpret_cast<const float4*>(consts.k1 + c0),
-                                            reinterpret_cast<const float4*>(consts.bdiv + c0),
-                                            reinterpret_cast<const float4*>(consts.mult + c0), fast, args.zp_out,
-                                            args.lo, packed);
-          *reinterpret_cast<uint4*>(out_px + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        };
-        switch (part) {
-          case 0: do_part(std::integral_constant<int, 0>{}); break;
-          case 1: do_part(std::integral_constant<int, 1>{}); break;
-          case 2: do_part(std::integral_constant<int, 2>{}); break;
-          default: do_part(std::integral_constant<int, 3>{}); break;
-        }
+        epi16_block<CHECK>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, (int64_t)C1_IMG * C1_COUT, true, release);
       }
     }
   }

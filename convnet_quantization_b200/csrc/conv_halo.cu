@@ -15,7 +15,7 @@
 // of one image row and its stride between groups (SBO) is one image row (P positions).  Accumulator row m = 8*g + j is
 // pixel (r0+g, c0+j), which has three consequences: (1) tiles cover the image exactly - no pad rows are computed;
 // (2) a TMEM lane quarter (32 rows = one epilogue warp) holds 4 image rows x 8 columns, i.e. whole 2x2 pooling
-// windows, so the fused max-pool is two warp shuffles on packed bytes - no shared-memory staging, no block barrier;
+// windows, so the fused max-pool needs no shared-memory staging and no block barrier (epilogue16.cuh);
 // (3) epilogue warps never talk to each other, only to the MMA issuer through the TMEM full/empty barriers of FOUR
 // accumulator slots, so a slow warp does not hold the others back and the issuer runs up to three tiles ahead.
 //
@@ -31,21 +31,26 @@
 // registers), and the accumulators are pre-biased in TMEM (common.cuh requant4_prebiased) so the arithmetic needs no
 // integer->float conversion.
 //
-// Warp roles (576 threads): warps 0..15 = epilogue (four per TMEM lane quarter, a quarter of the channels each),
-// warp 16 = loader, warp 17 = MMA issuer / TMEM owner (highest warp id = highest arbitration priority).
+// Warp roles (576 threads): warps 0..15 = epilogue (epilogue16.cuh: a warp drains one TMEM lane quarter x 64 channels
+// of a tile; sets of warps take alternate tiles), warp 16 = loader (activations AND the weights, whose rows are stored in
+// the epilogue's channel permutation), warp 17 = MMA issuer / TMEM owner (highest warp id = highest arbitration priority).
 #include <type_traits>
 
 #include "common.cuh"
+#include "epilogue16.cuh"
 
 namespace b200q {
 
-constexpr int HALO_EPI_WARPS = 16;
-constexpr int HALO_THREADS = 64 + 32 * HALO_EPI_WARPS;
-constexpr int HALO_LOAD_WARP = HALO_EPI_WARPS, HALO_MMA_WARP = HALO_EPI_WARPS + 1;
+// Epilogue warps per CTA (template parameter EW): 8 or 16.  16 warps + loader + issuer = 18 warps cap the kernel at
+// 96 registers per thread (five warps on one SM sub-partition), 8 + 2 leave 168.
+#ifndef B200Q_HALO_EPI_WARPS
+#define B200Q_HALO_EPI_WARPS 8
+#endif
 constexpr int HALO_SLOTS = 4;  // TMEM accumulator slots
 
-template <int IMG, int CIN_, int COUT, int NBI, bool POOL>
+template <int IMG, int CIN_, int COUT, int NBI, bool POOL, int EW>
 struct HaloCfg {
+  static constexpr int EPI_WARPS = EW, THREADS = 64 + 32 * EW, LOAD_WARP = EW, MMA_WARP = EW + 1;
   static constexpr int CIN = CIN_;               // bytes per pixel row == swizzle span (SWIZZLE_64B / SWIZZLE_128B)
   static constexpr int P = IMG + 1;              // pitch of the padded pixel sequence
   static constexpr int POS_PER_IMG = (IMG + 1) * P;
@@ -59,8 +64,12 @@ struct HaloCfg {
   static constexpr int W_BYTES = 9 * W_TAP_BYTES;
   static constexpr int SMEM_BYTES = 2 * A_BYTES + W_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
   static constexpr int TMEM_COLS = HALO_SLOTS * COUT;
-  static constexpr int COLS_PER_WARP = COUT / (HALO_EPI_WARPS / 4);
-  static constexpr int UNITS_PER_WARP = COLS_PER_WARP / 16;   // the epilogue works in units of 16 channels
+  // epilogue (epilogue16.cuh): a warp owns one TMEM lane quarter and one 64-channel part; the warps are grouped in
+  // SETS that take alternate tiles (set s handles the tiles with acc_it % SETS == s, i.e. slots s, s + SETS, ...)
+  static constexpr int PARTS = COUT / 64;
+  static constexpr int SETS = EW / 4 / PARTS;
+  static_assert(EW % (4 * PARTS) == 0 && SETS >= 1, "epilogue warps");
+  static_assert(HALO_SLOTS % SETS == 0, "a set must always meet the same slots");
   static_assert(COUT == 64 || COUT == 128, "COUT");
   static_assert(CIN == 64 || CIN == 128, "CIN");
   static_assert(IMG % TILE_ROWS == 0 && IMG % TILE_COLS == 0, "tiles must cover the image exactly");
@@ -71,13 +80,14 @@ struct HaloCfg {
 struct HaloArgs {
   const uint8_t* x;
   uint8_t* y;
+  const int8_t* w;     // [COUT][9][CIN]
   int64_t n_img;
   int num_bands;
   int zp_x;            // activation zero-point held by the pad positions
   int zp_out, lo;
   int bounded;
   int debug;           // B200Q_HALO_DEBUG bits (timing experiments only; results are wrong when set):
-                       //   1 = epilogue skips arithmetic and stores, 2 = MMA issuer skips the MMAs
+                       //   2 = MMA issuer skips the MMAs
 };
 
 // Per-output-channel constants, passed by value as a kernel parameter (constant bank).
@@ -89,18 +99,11 @@ struct alignas(16) HaloConsts {
   float mult[COUT];
 };
 
-// Per-byte max of two packed uint8x4 words (16-bit lanes are native, bytes are not).
-__device__ __forceinline__ uint32_t max2_u8x4(uint32_t a, uint32_t b) {
-  const uint32_t e = max_u16x2(__byte_perm(a, 0, 0x4240), __byte_perm(b, 0, 0x4240));
-  const uint32_t o = max_u16x2(__byte_perm(a, 0, 0x4341), __byte_perm(b, 0, 0x4341));
-  return __byte_perm(e, o, 0x6240);
-}
-
-template <int IMG, int CIN, int COUT, int NBI, bool POOL, bool CHECK>
-__global__ void __launch_bounds__(HALO_THREADS, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ HaloConsts<COUT> consts,
-                 const HaloArgs args) {
-  using C = HaloCfg<IMG, CIN, COUT, NBI, POOL>;
+template <int IMG, int CIN, int COUT, int NBI, bool POOL, bool CHECK, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
+conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs args) {
+  using C = HaloCfg<IMG, CIN, COUT, NBI, POOL, EW>;
+  constexpr int HALO_EPI_WARPS = C::EPI_WARPS, HALO_LOAD_WARP = C::LOAD_WARP, HALO_MMA_WARP = C::MMA_WARP;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_smem = smem;                                  // 2 x A_BYTES
@@ -116,16 +119,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   const int lane = threadIdx.x & 31;
 
   if (warp == HALO_LOAD_WARP && lane == 0) {
-    tma_prefetch_desc(&map_w);
     for (int i = 0; i < 2; ++i) {
       mbar_init(full_bar + i, 32);  // one cp.async-completion arrive per loader lane
       mbar_init(empty_bar + i, 1);
     }
     for (int i = 0; i < HALO_SLOTS; ++i) {
       mbar_init(tmem_full_bar + i, 1);
-      mbar_init(tmem_empty_bar + i, HALO_EPI_WARPS);
+      mbar_init(tmem_empty_bar + i, 4 * C::PARTS);  // the warps of the one set that drains this slot
     }
-    mbar_init(w_bar, 1);
+    mbar_init(w_bar, 32);  // one cp.async-completion arrive per loader lane
     fence_barrier_init();
   }
   if (warp == HALO_MMA_WARP) {
@@ -159,10 +161,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   const uint32_t tmem_base = *tmem_base_smem;
   // Accumulators start at MAGIC_BITS instead of 0 (every MMA accumulates): see requant4_prebiased.  Each epilogue
   // warp arms its own lane quarter / column slice of every slot here, and re-arms a unit right after reading it.
-  if (warp < HALO_EPI_WARPS) {
-    const uint32_t base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * C::COLS_PER_WARP;
+  if (warp < 4 * C::PARTS) {
+    const uint32_t base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 64;
     for (int slot = 0; slot < HALO_SLOTS; ++slot)
-      for (int c = 0; c < C::COLS_PER_WARP; c += 8) tmem_st_fill8(base + slot * COUT + c, MAGIC_BITS);
+      for (int c = 0; c < 64; c += 8) tmem_st_fill8(base + slot * COUT + c, MAGIC_BITS);
     tmem_st_wait();
   }
   tc_fence_before();
@@ -171,10 +173,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
 
   if (warp == HALO_LOAD_WARP) {
     // ================================================================== loader warp
-    if (lane == 0) {
-      mbar_expect_tx(w_bar, C::W_BYTES);
-      for (int tap = 0; tap < 9; ++tap)
-        tma_load_2d(w_smem + tap * C::W_TAP_BYTES, &map_w, w_bar, tap * C::CIN, 0);
+    // Weights, once: global [COUT][9][CIN] -> nine [COUT][CIN] K-major swizzled tap blocks whose ROW n holds output
+    // channel epi16_channel_of_column(n) (the epilogue's thread <-> channel assignment, epilogue16.cuh).
+    {
+      constexpr int CPR = C::CIN / 16;  // 16-byte chunks per row
+      const uint32_t w_base = smem_u32(w_smem);
+      for (int g = lane; g < 9 * COUT * CPR; g += 32) {
+        const int part = g % CPR, n = (g / CPR) % COUT, tap = g / (CPR * COUT);
+        const int swz = (C::CIN == 64) ? ((n >> 1) & 3) : (n & 7);
+        const uint32_t dst = w_base + tap * C::W_TAP_BYTES + n * C::CIN + ((part ^ swz) << 4);
+        const int8_t* src = args.w + ((int64_t)epi16_channel_of_column(n) * 9 + tap) * C::CIN + part * 16;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(w_bar)) : "memory");
     }
     // 16-byte chunk g of an image: global offset g*16 (linear), pixel g/(CIN/16) = (h, w), part g%(CIN/16);
     // shared: position (h+1)*P + (w+1) of the image's slot, chunk slot part ^ swz(pos): address bits [7,9) (64-byte
@@ -209,6 +220,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
     const bool leader = elect_one() != 0;
     constexpr uint32_t idesc = make_idesc_i8(128, COUT);
     mbar_wait(w_bar, 0);
+    fence_proxy_async_smem();
     const uint64_t w_desc0 = make_kmajor_desc<C::CIN>(smem_u32(w_smem), 8 * C::CIN);
     int it = 0, acc_it = 0;
     for (int band = blockIdx.x; band < args.num_bands; band += gridDim.x, ++it) {
@@ -248,69 +260,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   } else {
     // ================================================================== epilogue warps (independent of each other)
     const int quarter = warp & 3;
-    const int part = warp >> 2;               // which slice of COLS_PER_WARP channels
-    const int g_row = quarter * 4 + (lane >> 3), g_col = lane & 7;  // accumulator row 32*quarter + lane = pixel (g_row, g_col)
+    const int part = (warp >> 2) % C::PARTS;   // 64-channel part
+    const int set = (warp >> 2) / C::PARTS;    // takes the tiles with acc_it % SETS == set
+    const int j = lane >> 2;                   // column of the 8-column block this thread works on
+    const int ch0 = 64 * part + 16 * (lane & 3);
     const bool fast = args.bounded != 0;
-    int acc_it = 0;
-    for (int band = blockIdx.x; band < args.num_bands; band += gridDim.x) {
-      for (int t = 0; t < C::TILES; ++t, ++acc_it) {
+    Epi16Regs K;
+    epi16_init(consts, ch0, K);
+    int acc_base = 0;
+    for (int band = blockIdx.x; band < args.num_bands; band += gridDim.x, acc_base += C::TILES) {
+      // first tile of this band that belongs to the set: acc_it = acc_base + t  with  acc_it % SETS == set
+      for (int t = (set - acc_base % C::SETS + C::SETS) % C::SETS; t < C::TILES; t += C::SETS) {
+        const int acc_it = acc_base + t;
         const uint32_t slot = acc_it % HALO_SLOTS;
         const int bi = t / (C::TILES_X * C::TILES_Y), tt = t % (C::TILES_X * C::TILES_Y);
-        const int r = (tt / C::TILES_X) * C::TILE_ROWS + g_row, c = (tt % C::TILES_X) * C::TILE_COLS + g_col;
+        const int r0 = (tt / C::TILES_X) * C::TILE_ROWS + 4 * quarter, c = (tt % C::TILES_X) * C::TILE_COLS + j;
         const int64_t img = (int64_t)band * NBI + bi;
         const bool valid = img < args.n_img;
-        uint8_t* out_px;
-        if constexpr (POOL)
-          out_px = args.y + ((img * (IMG / 2) + (r >> 1)) * (IMG / 2) + (c >> 1)) * (int64_t)COUT;
-        else
-          out_px = args.y + ((img * IMG + r) * IMG + c) * (int64_t)COUT;
-
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * COUT + 64 * part;
+        auto release = [&]() {
+          if (lane == 0) mbar_arrive(tmem_empty_bar + slot);
+        };
         mbar_wait(tmem_full_bar + slot, (acc_it / HALO_SLOTS) & 1);
         tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * COUT;
-        // `part` is warp-uniform: dispatch once so that every constant below has a compile-time parameter offset
-        auto do_part = [&](auto part_tag) {
-          constexpr int N0 = decltype(part_tag)::value * C::COLS_PER_WARP;
-#pragma unroll
-          for (int u = 0; u < C::UNITS_PER_WARP; ++u) {
-            const int c0 = N0 + u * 16;
-            uint32_t v[16];
-            tmem_ld_32x16(t_row + c0, v);
-            tmem_ld_wait();
-            tmem_st_fill8(t_row + c0, MAGIC_BITS);  // re-arm for the tile that reuses this slot
-            tmem_st_fill8(t_row + c0 + 8, MAGIC_BITS);
-            if (u == C::UNITS_PER_WARP - 1) {
-              tmem_st_wait();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(tmem_empty_bar + slot);
-            }
-            if (args.debug & 1) continue;
-            uint32_t packed[4];
-            requant_chunk_prebiased<CHECK, 4>(v, reinterpret_cast<const int4*>(consts.cm + c0),
-                                              reinterpret_cast<const float4*>(consts.k1 + c0),
-                                              reinterpret_cast<const float4*>(consts.bdiv + c0),
-                                              reinterpret_cast<const float4*>(consts.mult + c0), fast, args.zp_out,
-                                              args.lo, packed);
-            if constexpr (POOL) {
-              // 2x2 window = lanes {l, l^1 (next column), l^8 (next row), l^9}; max commutes with the requantisation
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                packed[i] = max2_u8x4(packed[i], __shfl_xor_sync(0xffffffffu, packed[i], 1));
-                packed[i] = max2_u8x4(packed[i], __shfl_xor_sync(0xffffffffu, packed[i], 8));
-              }
-              if (valid && (lane & 9) == 0)
-                *reinterpret_cast<uint4*>(out_px + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            } else {
-              if (valid) *reinterpret_cast<uint4*>(out_px + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            }
-          }
-        };
-        switch (part) {
-          case 0: do_part(std::integral_constant<int, 0>{}); break;
-          case 1: do_part(std::integral_constant<int, 1>{}); break;
-          case 2: do_part(std::integral_constant<int, 2>{}); break;
-          default: do_part(std::integral_constant<int, 3>{}); break;
+        if constexpr (POOL) {
+          uint8_t* out = args.y + ((img * (IMG / 2) + (r0 >> 1) + (j & 1)) * (IMG / 2) + (c >> 1)) * (int64_t)COUT + ch0;
+          epi16_block_pool<CHECK>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, valid, lane, release);
+        } else {
+          uint8_t* out = args.y + ((img * IMG + r0) * IMG + c) * (int64_t)COUT + ch0;
+          epi16_block<CHECK>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, (int64_t)IMG * COUT, valid, release);
         }
       }
     }
@@ -324,22 +302,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   }
 }
 
-template <int IMG, int CIN, int COUT, int NBI, bool POOL, bool CHECK = true>
+template <int IMG, int CIN, int COUT, int NBI, bool POOL, bool CHECK = true, int EW = B200Q_HALO_EPI_WARPS>
 static int launch_halo(const uint8_t* x, uint8_t* y, int64_t n_img, const b200q_conv3x3* L, cudaStream_t stream) {
-  using C = HaloCfg<IMG, CIN, COUT, NBI, POOL>;
+  using C = HaloCfg<IMG, CIN, COUT, NBI, POOL, EW>;
   const b200q_requant& rq = L->rq;
-  if constexpr (CHECK && COUT == 64) {
+  if constexpr (CHECK) {  // drop the per-element range test when it is provably idle
     if ((rq.flags & B200Q_RQ_BOUNDED) && (rq.flags & B200Q_RQ_ACC22))
-      return launch_halo<IMG, CIN, COUT, NBI, POOL, false>(x, y, n_img, L, stream);
-  }
-  CUtensorMap map_w;
-  {
-    const uint64_t ktot = 9ull * C::CIN;
-    const uint64_t dims[2] = {ktot, (uint64_t)COUT};
-    const uint64_t strides[1] = {ktot};
-    const uint32_t box[2] = {(uint32_t)C::CIN, (uint32_t)COUT};
-    int rc = encode_tensor_map(&map_w, L->w, 2, dims, strides, box, C::CIN);
-    if (rc) return rc;
+      return launch_halo<IMG, CIN, COUT, NBI, POOL, false, EW>(x, y, n_img, L, stream);
   }
   HaloConsts<COUT> consts;
   for (int c = 0; c < COUT; ++c) {
@@ -349,7 +318,7 @@ static int launch_halo(const uint8_t* x, uint8_t* y, int64_t n_img, const b200q_
     consts.bdiv[c] = rq.bdiv_host[c];
     consts.mult[c] = rq.mult_host[c];
   }
-  auto kernel = conv_halo_kernel<IMG, CIN, COUT, NBI, POOL, CHECK>;
+  auto kernel = conv_halo_kernel<IMG, CIN, COUT, NBI, POOL, CHECK, EW>;
   static bool attr_set = false;
   if (!attr_set) {
     B200Q_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -361,10 +330,14 @@ static int launch_halo(const uint8_t* x, uint8_t* y, int64_t n_img, const b200q_
     const char* e = getenv("B200Q_HALO_DEBUG");
     debug = e ? atoi(e) : 0;
   }
-  HaloArgs args{x,    y,     n_img,     num_bands, L->zp_x, rq.zp_out, rq.relu ? rq.zp_out : 0, (rq.flags & B200Q_RQ_BOUNDED) ? 1 : 0,
+  HaloArgs args{x,        y,
+                L->w,     n_img,
+                num_bands, L->zp_x,
+                rq.zp_out, rq.relu ? rq.zp_out : 0,
+                (rq.flags & B200Q_RQ_BOUNDED) ? 1 : 0,
                 debug};
   const int grid = num_bands < num_sms() ? num_bands : num_sms();
-  kernel<<<grid, HALO_THREADS, C::SMEM_BYTES, stream>>>(map_w, consts, args);
+  kernel<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(consts, args);
   return launched("conv_halo_kernel");
 }
 
@@ -373,18 +346,28 @@ int conv3x3_halo_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_c
                           int* rc) {
   // needs the host mirrors of the per-channel constants (they become kernel parameters)
   if (!L->corr_host || !L->rq.mult_host || !L->rq.bdiv_host) return 1;
+  // B200Q_HALO_EW=16 selects the 16-epilogue-warp instantiations (A-B timing only)
+  static int ew = -1;
+  if (ew < 0) {
+    const char* e = getenv("B200Q_HALO_EW");
+    ew = e ? atoi(e) : B200Q_HALO_EPI_WARPS;
+  }
+#define B200Q_HALO_CASE(IMG_, CIN_, COUT_, NBI_, POOL_)                                                  \
+  (ew == 16 ? launch_halo<IMG_, CIN_, COUT_, NBI_, POOL_, true, 16>(x, y, b, L, s)                       \
+            : launch_halo<IMG_, CIN_, COUT_, NBI_, POOL_, true, 8>(x, y, b, L, s))
   if (L->img == 32 && L->cin == 64 && L->cout == 64) {
-    *rc = pool ? launch_halo<32, 64, 64, 1, true>(x, y, b, L, s) : launch_halo<32, 64, 64, 1, false>(x, y, b, L, s);
+    *rc = pool ? B200Q_HALO_CASE(32, 64, 64, 1, true) : B200Q_HALO_CASE(32, 64, 64, 1, false);
     return 0;
   }
   if (L->img == 16 && L->cin == 64 && L->cout == 128 && !pool) {
-    *rc = launch_halo<16, 64, 128, 3, false>(x, y, b, L, s);
+    *rc = B200Q_HALO_CASE(16, 64, 128, 3, false);
     return 0;
   }
   if (L->img == 16 && L->cin == 128 && L->cout == 128) {  // weights (144 KiB) + two single-image bands
-    *rc = pool ? launch_halo<16, 128, 128, 1, true>(x, y, b, L, s) : launch_halo<16, 128, 128, 1, false>(x, y, b, L, s);
+    *rc = pool ? B200Q_HALO_CASE(16, 128, 128, 1, true) : B200Q_HALO_CASE(16, 128, 128, 1, false);
     return 0;
   }
+#undef B200Q_HALO_CASE
   return 1;
 }
 
