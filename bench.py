@@ -257,6 +257,11 @@ def run_ours(args):
                 "net_int8_tops": OPS_PER_IMAGE * B / (total_stage_ms * 1e-3) / 1e12,
                 "stages": stages}
 
+    if args.stages_only:  # kernel-timing experiments (scripts/gpu_debug_modes.sh): no e2e leg, no parity assertion
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms / args.steps, "roofline": roofline}), flush=True)
+        return 0
+
     # ---- end to end through the reference-facing model object: pinned host input -> host logits
     x_host = x.cpu().pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
@@ -315,6 +320,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16384, help="images per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stages-only", action="store_true", help="print only the per-kernel table (timing experiments)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "ours" and world != args.gpus and args.gpus > 1:

@@ -135,13 +135,14 @@ def load(build_if_missing: bool = False) -> C.CDLL:
         return _lib
     if build_if_missing and _stale():
         build()
-    if not LIB_PATH.exists():
-        raise B200QError(f"{LIB_PATH} is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+    path = Path(os.environ.get("B200Q_LIB", LIB_PATH))  # B200Q_LIB: A-B timing of two builds (development only)
+    if not path.exists():
+        raise B200QError(f"{path} is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
                          "(there is no CPU fallback for the CUDA path)")
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(path))
     for name in EXPORTS:
         if not hasattr(lib, name):
-            raise B200QError(f"{LIB_PATH} does not export {name}")
+            raise B200QError(f"{path} does not export {name}")
     lib.b200q_last_error.restype = C.c_char_p
     lib.b200q_last_error.argtypes = []
     lib.b200q_abi_version.restype = C.c_int

@@ -101,10 +101,10 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
       if (r == 0 || r == C1_QP - 1 || c == 0 || c == C1_QP - 1) q_img[i] = zp4;
     }
     // weights [64][9][4] -> B operand [64][k = tap*3 + ch] (32-byte rows, SWIZZLE_32B), zero for k >= 27; row nr holds
-    // output channel epi16_channel_of_column(nr) (the epilogue's thread <-> channel assignment)
+    // output channel epi_channel_of_column<16>(nr) (the epilogue's thread <-> channel assignment)
     for (int i = t; i < C1_COUT * (C1_KB / 4); i += 32 * C1_EPI_WARPS) {
       const int nr = i / (C1_KB / 4), wd = i % (C1_KB / 4);
-      const int n = epi16_channel_of_column(nr);
+      const int n = epi_channel_of_column<16>(nr);
       uint32_t word = 0;
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
@@ -137,19 +137,24 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
     const int p = threadIdx.x - 32 * C1_PROD_WARP0;
     const int zp_sub = args.zp_x - (int)MAGIC_BITS;
     const uint32_t zp_hi = (uint32_t)args.zp_x << 24;
-    for (int it = 0; it < my_imgs; ++it) {
+    // thread p owns image row p/4, columns 8*(p%4) .. +7 of the fp32 planes.  The loads of image it+1 are issued right
+    // after image it has been quantised, so their HBM latency overlaps the im2col pass and the barrier waits.
+    const int row = p >> 2, col0 = (p & 3) * 8;
+    float4 v[3][2];
+    auto load_image = [&](int it) {
       const int64_t img = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
-      const int buf = it & 1;
-      // ---- (1) quantise: thread p owns image row p/4, columns 8*(p%4) .. +7
-      {
-        const int row = p >> 2, col0 = (p & 3) * 8;
-        const float* src = args.x + img * (3 * C1_IMG * C1_IMG) + row * C1_IMG + col0;
-        float4 v[3][2];
+      const float* src = args.x + img * (3 * C1_IMG * C1_IMG) + row * C1_IMG + col0;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          v[ch][0] = __ldg(reinterpret_cast<const float4*>(src + ch * C1_IMG * C1_IMG));
-          v[ch][1] = __ldg(reinterpret_cast<const float4*>(src + ch * C1_IMG * C1_IMG) + 1);
-        }
+      for (int ch = 0; ch < 3; ++ch) {
+        v[ch][0] = __ldg(reinterpret_cast<const float4*>(src + ch * C1_IMG * C1_IMG));
+        v[ch][1] = __ldg(reinterpret_cast<const float4*>(src + ch * C1_IMG * C1_IMG) + 1);
+      }
+    };
+    if (my_imgs > 0) load_image(0);
+    for (int it = 0; it < my_imgs; ++it) {
+      const int buf = it & 1;
+      // ---- (1) quantise
+      {
         uint32_t* dst = q_img + (row + 1) * C1_QP + col0 + 1;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -163,6 +168,7 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
                              (quantize_magic(c2[j], args.inv_scale, zp_sub) << 16) | zp_hi;
         }
       }
+      if (it + 1 < my_imgs) load_image(it + 1);
       asm volatile("bar.sync 2, %0;" ::"n"(32 * C1_PROD_WARPS) : "memory");
       // ---- (2) im2col rows: thread p builds row p of every tile; tile i = block (i/4, i%4), row p = pixel (p/8, p%8)
       mbar_wait(empty_bar + buf, ((it >> 1) & 1) ^ 1);
@@ -219,8 +225,8 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
     const int j = lane >> 2;                   // column of the 8-column block
     const int ch0 = 16 * (lane & 3);
     const bool fast = args.bounded != 0;
-    Epi16Regs K;
-    epi16_init(consts, ch0, K);
+    EpiRegs<16> K;
+    epi_init(consts, ch0, K);
     static_assert(C1_TILES % C1_SETS == 0 && C1_SLOTS % C1_SETS == 0, "sets");
     for (int it = 0; it < my_imgs; ++it) {
       const int64_t img = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
@@ -235,7 +241,7 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
         };
         mbar_wait(tmem_full_bar + slot, (acc_it / C1_SLOTS) & 1);
         tc_fence_after();
-        epi16_block<CHECK>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, (int64_t)C1_IMG * C1_COUT, true, release);
+        epi_block<CHECK, 16, /*SPLIT=*/true>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, (int64_t)C1_IMG * C1_COUT, true, release);
       }
     }
   }

@@ -31,9 +31,10 @@
 // registers), and the accumulators are pre-biased in TMEM (common.cuh requant4_prebiased) so the arithmetic needs no
 // integer->float conversion.
 //
-// Warp roles (576 threads): warps 0..15 = epilogue (epilogue16.cuh: a warp drains one TMEM lane quarter x 64 channels
+// Warp roles: warps 0..15 = epilogue (epilogue16.cuh: a warp drains one TMEM lane quarter x 64 channels
 // of a tile; sets of warps take alternate tiles), warp 16 = loader (activations AND the weights, whose rows are stored in
-// the epilogue's channel permutation), warp 17 = MMA issuer / TMEM owner (highest warp id = highest arbitration priority).
+// the epilogue's channel permutation), then two MMA issuer warps taking alternate tiles (the first owns the TMEM allocation; highest warp ids = highest
+// arbitration priority).
 #include <type_traits>
 
 #include "common.cuh"
@@ -41,16 +42,18 @@
 
 namespace b200q {
 
-// Epilogue warps per CTA (template parameter EW): 8 or 16.  16 warps + loader + issuer = 18 warps cap the kernel at
-// 96 registers per thread (five warps on one SM sub-partition), 8 + 2 leave 168.
-#ifndef B200Q_HALO_EPI_WARPS
-#define B200Q_HALO_EPI_WARPS 8
-#endif
+// Epilogue warps per CTA (template parameter EW): 16 warps whose threads own 8 output channels each (the 19 warps of the
+// CTA cap the kernel at 96 registers per thread: five warps on one SM sub-partition), or 8 warps x 16 channels.
 constexpr int HALO_SLOTS = 4;  // TMEM accumulator slots
+// Two MMA issuer warps take alternate tiles.  tools/probe_sbo.cu (chain probe): the tensor pipe does not buffer enough
+// MMAs to cover the issuer's per-tile work (slot wait, descriptor set-up, commit: ~200-290 cycles against 864 cycles
+// of MMAs per conv2 tile), so with one issuer it idled 20-25 % of the time; with two, one is always issuing.
+constexpr int HALO_ISSUERS = 2;
 
 template <int IMG, int CIN_, int COUT, int NBI, bool POOL, int EW>
 struct HaloCfg {
-  static constexpr int EPI_WARPS = EW, THREADS = 64 + 32 * EW, LOAD_WARP = EW, MMA_WARP = EW + 1;
+  // warps: EW epilogue, 1 loader, HALO_ISSUERS MMA issuers (the first one owns the TMEM allocation)
+  static constexpr int EPI_WARPS = EW, THREADS = 32 * (EW + 1 + HALO_ISSUERS), LOAD_WARP = EW, MMA_WARP = EW + 1;
   static constexpr int CIN = CIN_;               // bytes per pixel row == swizzle span (SWIZZLE_64B / SWIZZLE_128B)
   static constexpr int P = IMG + 1;              // pitch of the padded pixel sequence
   static constexpr int POS_PER_IMG = (IMG + 1) * P;
@@ -64,9 +67,11 @@ struct HaloCfg {
   static constexpr int W_BYTES = 9 * W_TAP_BYTES;
   static constexpr int SMEM_BYTES = 2 * A_BYTES + W_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
   static constexpr int TMEM_COLS = HALO_SLOTS * COUT;
-  // epilogue (epilogue16.cuh): a warp owns one TMEM lane quarter and one 64-channel part; the warps are grouped in
+  // epilogue (epilogue16.cuh): a warp owns one TMEM lane quarter and one PARTW-channel part; the warps are grouped in
   // SETS that take alternate tiles (set s handles the tiles with acc_it % SETS == s, i.e. slots s, s + SETS, ...)
-  static constexpr int PARTS = COUT / 64;
+  static constexpr int NCH = EW == 16 ? 8 : 16;  // output channels per epilogue thread
+  static constexpr int PARTW = 4 * NCH;          // accumulator columns per epilogue warp
+  static constexpr int PARTS = COUT / PARTW;
   static constexpr int SETS = EW / 4 / PARTS;
   static_assert(EW % (4 * PARTS) == 0 && SETS >= 1, "epilogue warps");
   static_assert(HALO_SLOTS % SETS == 0, "a set must always meet the same slots");
@@ -87,7 +92,9 @@ struct HaloArgs {
   int zp_out, lo;
   int bounded;
   int debug;           // B200Q_HALO_DEBUG bits (timing experiments only; results are wrong when set):
-                       //   2 = MMA issuer skips the MMAs
+                       //   2 = MMA issuer skips the MMAs, 4 = loader skips the band copies,
+                       //   8 = epilogue only drains (no arithmetic, no stores),
+                       //   16 = block 0 prints its SM-clock cycles and wall nanoseconds (effective SM clock under load)
 };
 
 // Per-output-channel constants, passed by value as a kernel parameter (constant bank).
@@ -100,7 +107,7 @@ struct alignas(16) HaloConsts {
 };
 
 template <int IMG, int CIN, int COUT, int NBI, bool POOL, bool CHECK, int EW>
-__global__ void __launch_bounds__(64 + 32 * EW, 1)
+__global__ void __launch_bounds__(32 * (EW + 1 + HALO_ISSUERS), 1)
 conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs args) {
   using C = HaloCfg<IMG, CIN, COUT, NBI, POOL, EW>;
   constexpr int HALO_EPI_WARPS = C::EPI_WARPS, HALO_LOAD_WARP = C::LOAD_WARP, HALO_MMA_WARP = C::MMA_WARP;
@@ -117,11 +124,13 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const long long dbg_c0 = clock64();
+  const uint64_t dbg_t0 = globaltimer_ns();
 
   if (warp == HALO_LOAD_WARP && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(full_bar + i, 32);  // one cp.async-completion arrive per loader lane
-      mbar_init(empty_bar + i, 1);
+      mbar_init(empty_bar + i, HALO_ISSUERS);
     }
     for (int i = 0; i < HALO_SLOTS; ++i) {
       mbar_init(tmem_full_bar + i, 1);
@@ -162,9 +171,9 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
   // Accumulators start at MAGIC_BITS instead of 0 (every MMA accumulates): see requant4_prebiased.  Each epilogue
   // warp arms its own lane quarter / column slice of every slot here, and re-arms a unit right after reading it.
   if (warp < 4 * C::PARTS) {
-    const uint32_t base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 64;
+    const uint32_t base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * C::PARTW;
     for (int slot = 0; slot < HALO_SLOTS; ++slot)
-      for (int c = 0; c < 64; c += 8) tmem_st_fill8(base + slot * COUT + c, MAGIC_BITS);
+      for (int c = 0; c < C::PARTW; c += 8) tmem_st_fill8(base + slot * COUT + c, MAGIC_BITS);
     tmem_st_wait();
   }
   tc_fence_before();
@@ -174,7 +183,7 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
   if (warp == HALO_LOAD_WARP) {
     // ================================================================== loader warp
     // Weights, once: global [COUT][9][CIN] -> nine [COUT][CIN] K-major swizzled tap blocks whose ROW n holds output
-    // channel epi16_channel_of_column(n) (the epilogue's thread <-> channel assignment, epilogue16.cuh).
+    // channel epi_channel_of_column<NCH>(n) (the epilogue's thread <-> channel assignment, epilogue16.cuh).
     {
       constexpr int CPR = C::CIN / 16;  // 16-byte chunks per row
       const uint32_t w_base = smem_u32(w_smem);
@@ -182,7 +191,7 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
         const int part = g % CPR, n = (g / CPR) % COUT, tap = g / (CPR * COUT);
         const int swz = (C::CIN == 64) ? ((n >> 1) & 3) : (n & 7);
         const uint32_t dst = w_base + tap * C::W_TAP_BYTES + n * C::CIN + ((part ^ swz) << 4);
-        const int8_t* src = args.w + ((int64_t)epi16_channel_of_column(n) * 9 + tap) * C::CIN + part * 16;
+        const int8_t* src = args.w + ((int64_t)epi_channel_of_column<C::NCH>(n) * 9 + tap) * C::CIN + part * 16;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(w_bar)) : "memory");
@@ -199,7 +208,7 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
       const uint32_t a_buf = smem_u32(a_smem + buf * C::A_BYTES);
       for (int bi = 0; bi < NBI; ++bi) {
         const int64_t img = (int64_t)band * NBI + bi;
-        if (img >= args.n_img) break;  // stale data: those pixels are never stored
+        if (img >= args.n_img || (args.debug & 4)) break;  // stale data: those pixels are never stored
         const uint8_t* src = args.x + img * (int64_t)(IMG * IMG * C::CIN);
 #pragma unroll 8
         for (int g = lane; g < CHUNKS_PER_IMG; g += 32) {
@@ -213,16 +222,18 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
       // this lane's arrive fires when all of its copies above have landed (barrier count = 32 lanes)
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(full_bar + buf)) : "memory");
     }
-  } else if (warp == HALO_MMA_WARP) {
-    // ================================================================== MMA issuer
+  } else if (warp >= HALO_MMA_WARP) {
+    // ================================================================== MMA issuers (alternate tiles)
     // The whole warp walks the loop (uniform control flow, waits included); one elected lane issues the MMAs and
     // commits.  Descriptors are built once per band / tile; per MMA only compile-time offsets are added.
+    static_assert(C::TILES % HALO_ISSUERS == 0, "every issuer gets the same number of tiles per band");
+    const int issuer = warp - HALO_MMA_WARP;
     const bool leader = elect_one() != 0;
     constexpr uint32_t idesc = make_idesc_i8(128, COUT);
     mbar_wait(w_bar, 0);
     fence_proxy_async_smem();
     const uint64_t w_desc0 = make_kmajor_desc<C::CIN>(smem_u32(w_smem), 8 * C::CIN);
-    int it = 0, acc_it = 0;
+    int it = 0;
     for (int band = blockIdx.x; band < args.num_bands; band += gridDim.x, ++it) {
       const int buf = it & 1;
       mbar_wait(full_bar + buf, (it >> 1) & 1);
@@ -230,7 +241,8 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
       tc_fence_after();
       // 8-row core groups = 8 consecutive pixels of an image row; group stride (SBO) = one image row of the sequence
       const uint64_t a_desc0 = make_kmajor_desc<C::CIN>(smem_u32(a_smem + buf * C::A_BYTES), C::P * C::CIN);
-      for (int t = 0; t < C::TILES; ++t, ++acc_it) {
+      for (int t = issuer; t < C::TILES; t += HALO_ISSUERS) {
+        const int acc_it = it * C::TILES + t;
         const uint32_t slot = acc_it % HALO_SLOTS;
         mbar_wait(tmem_empty_bar + slot, ((acc_it / HALO_SLOTS) & 1) ^ 1);
         tc_fence_after();
@@ -254,19 +266,19 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
         }
         __syncwarp();
       }
-      if (leader) tc_commit(empty_bar + buf);  // arrives when every MMA that reads this band has completed
+      if (leader) tc_commit(empty_bar + buf);  // arrives when every MMA of this issuer that reads the band has completed
       __syncwarp();
     }
   } else {
     // ================================================================== epilogue warps (independent of each other)
     const int quarter = warp & 3;
-    const int part = (warp >> 2) % C::PARTS;   // 64-channel part
+    const int part = (warp >> 2) % C::PARTS;   // PARTW-channel part
     const int set = (warp >> 2) / C::PARTS;    // takes the tiles with acc_it % SETS == set
     const int j = lane >> 2;                   // column of the 8-column block this thread works on
-    const int ch0 = 64 * part + 16 * (lane & 3);
+    const int ch0 = C::PARTW * part + C::NCH * (lane & 3);
     const bool fast = args.bounded != 0;
-    Epi16Regs K;
-    epi16_init(consts, ch0, K);
+    EpiRegs<C::NCH> K;
+    epi_init(consts, ch0, K);
     int acc_base = 0;
     for (int band = blockIdx.x; band < args.num_bands; band += gridDim.x, acc_base += C::TILES) {
       // first tile of this band that belongs to the set: acc_it = acc_base + t  with  acc_it % SETS == set
@@ -277,18 +289,24 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
         const int r0 = (tt / C::TILES_X) * C::TILE_ROWS + 4 * quarter, c = (tt % C::TILES_X) * C::TILE_COLS + j;
         const int64_t img = (int64_t)band * NBI + bi;
         const bool valid = img < args.n_img;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * COUT + 64 * part;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * COUT + C::PARTW * part;
         auto release = [&]() {
           if (lane == 0) mbar_arrive(tmem_empty_bar + slot);
         };
         mbar_wait(tmem_full_bar + slot, (acc_it / HALO_SLOTS) & 1);
         tc_fence_after();
+        if (args.debug & 8) {
+          tc_fence_before();
+          __syncwarp();
+          release();
+          continue;
+        }
         if constexpr (POOL) {
           uint8_t* out = args.y + ((img * (IMG / 2) + (r0 >> 1) + (j & 1)) * (IMG / 2) + (c >> 1)) * (int64_t)COUT + ch0;
-          epi16_block_pool<CHECK>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, valid, lane, release);
+          epi_block_pool<CHECK>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, valid, lane, release);
         } else {
           uint8_t* out = args.y + ((img * IMG + r0) * IMG + c) * (int64_t)COUT + ch0;
-          epi16_block<CHECK>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, (int64_t)IMG * COUT, valid, release);
+          epi_block<CHECK>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, (int64_t)IMG * COUT, valid, release);
         }
       }
     }
@@ -296,13 +314,19 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
 
   tc_fence_before();
   __syncthreads();
+  if ((args.debug & 16) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long dc = clock64() - dbg_c0;
+    const uint64_t dt = globaltimer_ns() - dbg_t0;
+    printf("conv_halo<%d,%d,%d> block 0: %lld cycles in %llu ns = %.0f MHz\n", IMG, CIN, COUT, dc, (unsigned long long)dt,
+           1e3 * (double)dc / (double)dt);
+  }
   if (warp == HALO_MMA_WARP) {
     __syncwarp();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
-template <int IMG, int CIN, int COUT, int NBI, bool POOL, bool CHECK = true, int EW = B200Q_HALO_EPI_WARPS>
+template <int IMG, int CIN, int COUT, int NBI, bool POOL, bool CHECK = true, int EW = 8>
 static int launch_halo(const uint8_t* x, uint8_t* y, int64_t n_img, const b200q_conv3x3* L, cudaStream_t stream) {
   using C = HaloCfg<IMG, CIN, COUT, NBI, POOL, EW>;
   const b200q_requant& rq = L->rq;
@@ -346,25 +370,27 @@ int conv3x3_halo_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_c
                           int* rc) {
   // needs the host mirrors of the per-channel constants (they become kernel parameters)
   if (!L->corr_host || !L->rq.mult_host || !L->rq.bdiv_host) return 1;
-  // B200Q_HALO_EW=16 selects the 16-epilogue-warp instantiations (A-B timing only)
-  static int ew = -1;
-  if (ew < 0) {
+  // Epilogue warps per layer (measured, same box): 16 warps x 8 channels win by ~2 % on the pooled layers (conv2,
+  // conv4), 8 warps x 16 channels by ~20 % on conv3, whose unpooled 128-channel tiles keep all 16 warps on the same tile
+  // and multiply the mbarrier wake-ups.  B200Q_HALO_EW=8|16 overrides (A-B timing only).
+  static int ew_env = -1;
+  if (ew_env < 0) {
     const char* e = getenv("B200Q_HALO_EW");
-    ew = e ? atoi(e) : B200Q_HALO_EPI_WARPS;
+    ew_env = e ? atoi(e) : 0;
   }
-#define B200Q_HALO_CASE(IMG_, CIN_, COUT_, NBI_, POOL_)                                                  \
-  (ew == 16 ? launch_halo<IMG_, CIN_, COUT_, NBI_, POOL_, true, 16>(x, y, b, L, s)                       \
-            : launch_halo<IMG_, CIN_, COUT_, NBI_, POOL_, true, 8>(x, y, b, L, s))
+#define B200Q_HALO_CASE(IMG_, CIN_, COUT_, NBI_, POOL_, EW_DEFAULT)                                      \
+  ((ew_env ? ew_env : EW_DEFAULT) == 16 ? launch_halo<IMG_, CIN_, COUT_, NBI_, POOL_, true, 16>(x, y, b, L, s) \
+                                        : launch_halo<IMG_, CIN_, COUT_, NBI_, POOL_, true, 8>(x, y, b, L, s))
   if (L->img == 32 && L->cin == 64 && L->cout == 64) {
-    *rc = pool ? B200Q_HALO_CASE(32, 64, 64, 1, true) : B200Q_HALO_CASE(32, 64, 64, 1, false);
+    *rc = pool ? B200Q_HALO_CASE(32, 64, 64, 1, true, 16) : B200Q_HALO_CASE(32, 64, 64, 1, false, 8);
     return 0;
   }
   if (L->img == 16 && L->cin == 64 && L->cout == 128 && !pool) {
-    *rc = B200Q_HALO_CASE(16, 64, 128, 3, false);
+    *rc = B200Q_HALO_CASE(16, 64, 128, 3, false, 8);
     return 0;
   }
   if (L->img == 16 && L->cin == 128 && L->cout == 128) {  // weights (144 KiB) + two single-image bands
-    *rc = pool ? B200Q_HALO_CASE(16, 128, 128, 1, true) : B200Q_HALO_CASE(16, 128, 128, 1, false);
+    *rc = pool ? B200Q_HALO_CASE(16, 128, 128, 1, true, 16) : B200Q_HALO_CASE(16, 128, 128, 1, false, 8);
     return 0;
   }
 #undef B200Q_HALO_CASE
