@@ -169,6 +169,20 @@ def run_reference(args):
     return 0
 
 
+def ncu_traffic(stage: str, batch: int):
+    """DRAM bytes (read + written) per launch of `stage`, from the committed `ncu --set full` capture of one forward
+    at the same batch (profiles/r01_ncu_net.json, written by scripts/ncu_summary.py); None when no capture matches."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_net.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        if int(d["batch"]) != int(batch):
+            return None
+        return float(d["stages"][stage]["dram_bytes"])
+    except (OSError, KeyError, ValueError, TypeError):
+        return None
+
+
 # ----------------------------------------------------------------------------------------------- GPU leg
 def run_ours(args):
     import torch.distributed as dist
@@ -251,7 +265,7 @@ def run_ours(args):
     d = stages[dom]
     roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"],
                 "peak": int8_peak if d["bound"] == "tensor" else peaks["hbm_gbs"], "unit": d["unit"], "frac": d["frac"],
-                "traffic": None, "share_of_step": acc[dom] / total_stage_ms,
+                "traffic": ncu_traffic(dom, B), "share_of_step": acc[dom] / total_stage_ms,
                 "peak_source": (f"{peaks['source']}: 2 x bf16_tflops_sustained (int8 = 2x bf16 issue rate)"
                                 if d["bound"] == "tensor" else f"{peaks['source']}: hbm_gbs"),
                 "net_int8_tops": OPS_PER_IMAGE * B / (total_stage_ms * 1e-3) / 1e12,

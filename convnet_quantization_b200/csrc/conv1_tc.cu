@@ -241,7 +241,8 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
         };
         mbar_wait(tmem_full_bar + slot, (acc_it / C1_SLOTS) & 1);
         tc_fence_after();
-        epi_block<CHECK, 16, /*SPLIT=*/true>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, (int64_t)C1_IMG * C1_COUT, true, release);
+        epi_block<CHECK, 16, /*SPLIT=*/true>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, (int64_t)C1_IMG * C1_COUT,
+                                             2 * (int64_t)C1_IMG * C1_COUT, true, true, release);
       }
     }
   }

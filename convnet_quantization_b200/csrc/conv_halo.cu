@@ -306,7 +306,8 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
           epi_block_pool<CHECK>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, valid, lane, release);
         } else {
           uint8_t* out = args.y + ((img * IMG + r0) * IMG + c) * (int64_t)COUT + ch0;
-          epi_block<CHECK>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, (int64_t)IMG * COUT, valid, release);
+          epi_block<CHECK>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, (int64_t)IMG * COUT, 2 * (int64_t)IMG * COUT,
+                           valid, valid, release);
         }
       }
     }

@@ -152,15 +152,17 @@ __device__ __forceinline__ void epi_drain(uint32_t t_addr, EpiRegs<NCH>& K, uint
 
 // ---------------------------------------------------------------------------------------------------- no pooling
 // One warp, one 32-lane quarter x 4*NCH columns of an accumulator slot.  t_addr = tmem base + (quarter*32 << 16) +
-// first column.  Thread (j = lane/4, q = lane&3) produces channels ch0..ch0+NCH-1 of the pixels (row0 + i, col0 + j),
-// i = 0..3, of the block row this quarter covers; out = address of pixel (row0, col0 + j) channel ch0, row_stride =
-// bytes between image rows.  `release` is called (by all lanes, converged) once the slot has been read and re-armed.
+// first column.  Thread (j = lane/4, q = lane&3) produces channels ch0..ch0+NCH-1 of four pixels: accumulator rows
+// 16*half + 8*s + j of the quarter (half, s in 0..1), stored at out + half*stride_half + s*stride_s.  In the halo
+// kernels' single-image blocks these are image rows 2*half + s of the quarter (stride_s = one image row); in
+// conv_pair.cu s selects the image of the pair and half the image row.  valid0/valid1: store the s = 0 / 1 pixels.
+// `release` is called (by all lanes, converged) once the slot has been read and re-armed.
 // SPLIT: read, re-arm and process one 16-lane half at a time (half the live registers; the slot is handed back after the
 // second half has been read) - for kernels whose warp count leaves less than ~150 registers per thread.
 template <bool CHECK, int NCH, bool SPLIT = false, class Consts, class Release>
 __device__ __forceinline__ void epi_block(uint32_t t_addr, EpiRegs<NCH>& K, const Consts& consts, int ch0, bool fast,
-                                          int zp_out, int lo, uint8_t* out, int64_t row_stride, bool valid,
-                                          Release release) {
+                                          int zp_out, int lo, uint8_t* out, int64_t stride_s, int64_t stride_half,
+                                          bool valid0, bool valid1, Release release) {
   constexpr int G = NCH / 4, PARTW = 4 * NCH;
   const int zp_sub = zp_out - (int)MAGIC_BITS;
   uint32_t v[2][2 * NCH];
@@ -200,7 +202,7 @@ __device__ __forceinline__ void epi_block(uint32_t t_addr, EpiRegs<NCH>& K, cons
           packed[g] = epi_requant4_exact(w[0], w[1], w[4], w[5], consts, ch0 + 4 * g, zp_out, lo);
         }
       }
-      if (valid) epi_store<G>(out + (2 * half + s) * row_stride, packed);
+      if (s == 0 ? valid0 : valid1) epi_store<G>(out + half * stride_half + s * stride_s, packed);
     }
   }
 }
@@ -208,9 +210,11 @@ __device__ __forceinline__ void epi_block(uint32_t t_addr, EpiRegs<NCH>& K, cons
 // ---------------------------------------------------------------------------------------------------- 2x2 max-pool
 // Same block; the quarter's 4 image rows x 8 columns become 2 x 4 pooled pixels.  Thread (j, q) ends up with the pooled
 // pixel (pooled row j&1, pooled column j>>1) of the block, channels ch0..ch0+NCH-1; out = its address.
+// PAIRED (conv_pair.cu): the quarter holds image rows {2q, 2q+1} of TWO images (accumulator row 16*half + 8*image + j),
+// so the vertical maximum runs over the halves and thread (j, q) ends up with pooled column j>>1 of image j&1.
 // max() on the biased bit patterns is monotone in the raw accumulator (|acc| < 2^27), and the requantisation is
 // monotone non-decreasing in the accumulator, so pooling first equals aten::quantized_max_pool2d on the stored tensor.
-template <bool CHECK, int NCH, class Consts, class Release>
+template <bool CHECK, int NCH, bool PAIRED = false, class Consts, class Release>
 __device__ __forceinline__ void epi_block_pool(uint32_t t_addr, EpiRegs<NCH>& K, const Consts& consts, int ch0, bool fast,
                                                int zp_out, int lo, uint8_t* out, bool valid, int lane, Release release) {
   constexpr int G = NCH / 4;
@@ -222,8 +226,9 @@ __device__ __forceinline__ void epi_block_pool(uint32_t t_addr, EpiRegs<NCH>& K,
 #pragma unroll
   for (int k = 0; k < NCH; ++k) {  // k = 4u + 2b + e  <-  registers 8u + 4b + 2s + e
     const int i0 = 8 * (k >> 2) + 4 * ((k >> 1) & 1) + (k & 1);
-    const uint32_t m0 = max(v[0][i0], v[0][i0 + 2]);  // pooled row 0 of the block, column j
-    const uint32_t m1 = max(v[1][i0], v[1][i0 + 2]);  // pooled row 1
+    // pooled row 0 / 1 of the block (PAIRED: pooled row of image 0 / 1), column j
+    const uint32_t m0 = PAIRED ? max(v[0][i0], v[1][i0]) : max(v[0][i0], v[0][i0 + 2]);
+    const uint32_t m1 = PAIRED ? max(v[0][i0 + 2], v[1][i0 + 2]) : max(v[1][i0], v[1][i0 + 2]);
     const uint32_t send = odd ? m0 : m1;
     const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 4);
     r[k] = max(odd ? m1 : m0, recv);
