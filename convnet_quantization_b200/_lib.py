@@ -16,7 +16,8 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libb200q.so"
 BUILD_DIR = PKG_DIR / "build"
-SOURCES = ("runtime.cu", "elementwise.cu", "simt.cu", "igemm_tc.cu", "conv_halo.cu", "conv1_tc.cu", "net.cu")
+SOURCES = ("runtime.cu", "elementwise.cu", "simt.cu", "igemm_tc.cu", "conv_halo.cu", "conv_pair.cu", "conv1_tc.cu",
+           "net.cu")
 # -fmad=false: the requantisation is specified as separately rounded fp32 add / mul; ptxas was
 # seen contracting even explicit mul.rn.f32x2 + add.rn.f32x2 pairs into FFMA2, which changes the rounding.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

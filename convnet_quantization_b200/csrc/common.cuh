@@ -25,6 +25,9 @@ int conv1_tc_dispatch(const float* x, uint8_t* y, int64_t b, float inv_scale, co
                       int* rc);
 int conv3x3_halo_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, bool pool, cudaStream_t s,
                           int* rc);
+// conv_pair.cu: pair-interleaved halo kernel for the 8x8 layers (conv5, conv6); returns 1 when not covered
+int conv3x3_pair_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, bool pool, cudaStream_t s,
+                          int* rc);
 
 // ---------------------------------------------------------------- exact fbgemm requantisation
 // t = f32(acc) + bdiv; t = t * mult; q = clamp(rne(t) + zp, lo, 255).  Intrinsics forbid FMA contraction

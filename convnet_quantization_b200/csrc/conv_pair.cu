@@ -15,9 +15,11 @@
 //   147 / 295 KB of weights per band of 2 x 36 / 72 MMAs = 32 B/clk/SM.  The two channel halves of a band are computed
 //   by different CTAs, which costs a second read of the (small) activations and keeps the epilogue constants of a
 //   thread fixed for the lifetime of the CTA.
-// * The input channels are split in two K halves held in separate single-buffered arrays (row = KC = cin/2 bytes, the
-//   swizzle span).  The MMAs of a band run K half 0 first, then K half 1, so the loader refills half 0 with the next
-//   band while half 1 is being consumed, and vice versa: single buffering without a bubble.
+// * Shared-memory rows are KC = 128 bytes (the widest swizzle span; weight chunks of 64-byte rows made the TMA the
+//   bottleneck of conv5: 0.28 ms instead of 0.14).  conv6's 256 input channels are therefore two K halves held in
+//   separate arrays.  Its MMAs run K half 0 first, then K half 1, so with ONE buffer per half (two would not fit) the
+//   loader refills half 0 with the next band while half 1 is being consumed, and vice versa.  conv5 has one K "half"
+//   and double-buffers it.
 // * Weights stream through a ring of [128 channels][KC] chunks (one per K half and tap) filled by 5-D TMA boxes that
 //   deliver the rows in the epilogue's channel permutation (epilogue16.cuh).
 // * Warps: 8 epilogue (epilogue16.cuh, 16 channels per thread), activation loader, weight producer, two MMA issuers
@@ -36,17 +38,19 @@ constexpr int PAIR_T = 2;       // pairs (= tiles) per band
 
 template <int CIN>
 struct PairCfg {
-  static constexpr int KC = CIN / 2;                  // bytes per row of one K half == swizzle span
+  static constexpr int KC = 128;                      // bytes per row of one K half == swizzle span
+  static constexpr int KH = CIN / KC;                 // K halves: 1 (conv5) or 2 (conv6)
   static constexpr int P = 2 * PAIR_IMG + 2;          // 18: sequence pitch of an interleaved row
   static constexpr int PAIR_POS = (PAIR_IMG + 2) * P; // 180: pad row, 8 rows, pad row
   static constexpr int A_POS = PAIR_T * PAIR_POS + 8; // + the positions the last taps of the last tile reach
   static constexpr int A_BYTES = (A_POS * KC + 1023) / 1024 * 1024;   // one K half
+  static constexpr int ABUF = KH == 1 ? 2 : 1;                         // band buffers per K half
   static constexpr int B_BYTES = PAIR_N * KC;                          // one weight chunk: (K half, tap)
-  static constexpr int STAGES = KC == 64 ? 8 : 6;
-  static constexpr int CHUNKS = 2 * 9;                                 // weight chunks per band
-  static constexpr int SMEM_BYTES = 2 * A_BYTES + STAGES * B_BYTES + 512 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr int STAGES = 6;
+  static constexpr int CHUNKS = KH * 9;                                // weight chunks per band
+  static constexpr int SMEM_BYTES = KH * ABUF * A_BYTES + STAGES * B_BYTES + 512 /*barriers*/ + 1024 /*alignment slack*/;
   static constexpr int MMAS_PER_CHUNK = KC / 32;
-  static_assert(KC == 64 || KC == 128, "KC");
+  static_assert(CIN == 128 || CIN == 256, "CIN");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 };
 
@@ -82,11 +86,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   constexpr int IMG = PAIR_IMG, COUT = PAIR_COUT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* a_smem = smem;                                   // [2 K halves][A_BYTES]
-  uint8_t* b_smem = a_smem + 2 * C::A_BYTES;                // [STAGES][128][KC]
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(b_smem + C::STAGES * C::B_BYTES);  // [2]
-  uint64_t* a_empty = a_full + 2;                           // [2]
-  uint64_t* b_full = a_empty + 2;                           // [STAGES]
+  constexpr int NA = C::KH * C::ABUF;                       // activation arrays: index ab = KH*(band buffer) + K half
+  uint8_t* a_smem = smem;                                   // [NA][A_BYTES]
+  uint8_t* b_smem = a_smem + NA * C::A_BYTES;               // [STAGES][128][KC]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(b_smem + C::STAGES * C::B_BYTES);  // [NA]
+  uint64_t* a_empty = a_full + NA;                          // [NA]
+  uint64_t* b_full = a_empty + NA;                          // [STAGES]
   uint64_t* b_empty = b_full + C::STAGES;                   // [STAGES]
   uint64_t* tmem_full_bar = b_empty + C::STAGES;            // [PAIR_SLOTS]
   uint64_t* tmem_empty_bar = tmem_full_bar + PAIR_SLOTS;    // [PAIR_SLOTS]
@@ -99,7 +104,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
 
   if (warp == PAIR_W_WARP && lane == 0) {
     tma_prefetch_desc(&map_w);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NA; ++i) {
       mbar_init(a_full + i, 32);   // one cp.async-completion arrive per loader lane
       mbar_init(a_empty + i, 2);   // one commit per issuer
     }
@@ -123,8 +128,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
     const uint32_t zp4 = (uint32_t)args.zp_x * 0x01010101u;
     const uint4 zpv = make_uint4(zp4, zp4, zp4, zp4);
     constexpr int CPR = C::KC / 16;
-    for (int i = threadIdx.x; i < 2 * C::A_POS * CPR; i += 32 * PAIR_EPI_WARPS) {
-      const int kh = i / (C::A_POS * CPR), rem = i % (C::A_POS * CPR);
+    for (int i = threadIdx.x; i < NA * C::A_POS * CPR; i += 32 * PAIR_EPI_WARPS) {
+      const int kh = i / (C::A_POS * CPR), rem = i % (C::A_POS * CPR);  // kh: array index ab
       const int pos = rem / CPR, part = rem % CPR;
       const int in_pair = pos % C::PAIR_POS, rr = in_pair / C::P, cc = in_pair % C::P;
       const bool pad = pos >= PAIR_T * C::PAIR_POS || rr == 0 || rr == IMG + 1 || cc == 0 || cc == IMG + 1;
@@ -149,31 +154,37 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
 
   if (warp == PAIR_LOAD_WARP) {
     // ================================================================== activation loader
-    // 16-byte chunk g of (image, K half): pixel g / CPR = (h, w), part g % CPR; destination position
-    // pair*180 + (h+1)*18 + 9*image_in_pair + (w+1), chunk slot part ^ swz(position) (hardware swizzle on absolute
-    // addresses; the arrays are 1 KiB aligned)
-    constexpr int CPR = C::KC / 16;
-    constexpr int CHUNKS_PER_IMG = IMG * IMG * CPR;
+    // One warp iteration copies ROWS_PER_IT image rows: lane -> (row-in-iteration, pixel w, 16-byte part).  Destination:
+    // position pair*180 + (h+1)*18 + 9*image_in_pair + (w+1), chunk slot part ^ swz(position) (hardware swizzle on
+    // absolute addresses; the arrays are 1 KiB aligned).  Everything but the row offset is loop-invariant.
+    constexpr int CPR = C::KC / 16;                 // 16-byte chunks per pixel row of a K half
+    constexpr int ROWS_PER_IT = 32 / (IMG * CPR) > 0 ? 32 / (IMG * CPR) : 1;
+    constexpr int ITS_PER_ROW = IMG * CPR / 32 > 0 ? IMG * CPR / 32 : 1;   // KC = 128: two iterations per image row
+    const int part = lane % CPR;
+    const int w_it = (lane / CPR) % IMG, w_step = 32 / CPR;                // KC = 128: w = lane/8 + 4*iteration
+    const int h_it = lane / (IMG * CPR);                                   // KC = 64 only: 0 (32 lanes = one row)
     int it = 0;
     for (int band = band0; band < args.num_bands; band += band_step, ++it) {
-      for (int kh = 0; kh < 2; ++kh) {
-        mbar_wait(a_empty + kh, (it & 1) ^ 1);
-        const uint32_t a_buf = smem_u32(a_smem + kh * C::A_BYTES);
+      for (int kh = 0; kh < C::KH; ++kh) {
+        const int ab = (it % C::ABUF) * C::KH + kh;
+        mbar_wait(a_empty + ab, ((it / C::ABUF) & 1) ^ 1);
+        const uint32_t a_buf = smem_u32(a_smem + ab * C::A_BYTES);
         for (int bi = 0; bi < 2 * PAIR_T; ++bi) {
           const int64_t img = (int64_t)band * (2 * PAIR_T) + bi;
           if (img >= args.n_img) break;  // stale data: those pixels are never stored
-          const uint8_t* src = args.x + img * (int64_t)(IMG * IMG * CIN) + kh * C::KC;
-          const int pos0 = (bi >> 1) * C::PAIR_POS + (bi & 1) * (IMG + 1);
-#pragma unroll 4
-          for (int g = lane; g < CHUNKS_PER_IMG; g += 32) {
-            const int px = g / CPR, part = g % CPR;
-            const int pos = pos0 + (px / IMG + 1) * C::P + (px % IMG) + 1;
+          const uint8_t* src = args.x + img * (int64_t)(IMG * IMG * CIN) + kh * C::KC + part * 16;
+          const int pos0 = (bi >> 1) * C::PAIR_POS + (bi & 1) * (IMG + 1) + C::P + 1;  // pixel (0, 0)
+#pragma unroll
+          for (int i = 0; i < IMG * ITS_PER_ROW / ROWS_PER_IT; ++i) {
+            const int h = (i / ITS_PER_ROW) * ROWS_PER_IT + h_it;
+            const int w = w_it + (i % ITS_PER_ROW) * w_step;
+            const int pos = pos0 + h * C::P + w;
             const int swz = (C::KC == 64) ? ((pos >> 1) & 3) : (pos & 7);
             const uint32_t dst = a_buf + pos * C::KC + ((part ^ swz) << 4);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + px * CIN + part * 16) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (h * IMG + w) * CIN) : "memory");
           }
         }
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(a_full + kh)) : "memory");
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(a_full + ab)) : "memory");
       }
     }
   } else if (warp == PAIR_W_WARP) {
@@ -205,7 +216,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
     const uint64_t b_desc0 = make_kmajor_desc<C::KC>(smem_u32(b_smem), 8 * C::KC);
     // 8-row core groups = the 8 pixels of one image row; consecutive groups are 9 positions apart
     const uint64_t a_desc_tile =
-        make_kmajor_desc<C::KC>(smem_u32(a_smem) + issuer * C::PAIR_POS * C::KC, (IMG + 1) * C::KC);
+        make_kmajor_desc<C::KC>(smem_u32(a_smem) + issuer * C::PAIR_POS * C::KC, (IMG + 1) * C::KC);  // array 0
     uint32_t stage = 0, phase = 0;
     int it = 0;
     for (int band = band0; band < args.num_bands; band += band_step, ++it) {
@@ -214,11 +225,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       mbar_wait(tmem_empty_bar + slot, ((acc_it / PAIR_SLOTS) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + slot * PAIR_N;
-      for (int kh = 0; kh < 2; ++kh) {
-        mbar_wait(a_full + kh, it & 1);
+      for (int kh = 0; kh < C::KH; ++kh) {
+        const int ab = (it % C::ABUF) * C::KH + kh;
+        mbar_wait(a_full + ab, (it / C::ABUF) & 1);
         fence_proxy_async_smem();  // cp.async wrote through the generic proxy
         tc_fence_after();
-        const uint64_t a_desc_kh = a_desc_tile + (uint64_t)((kh * C::A_BYTES) >> 4);
+        const uint64_t a_desc_kh = a_desc_tile + (uint64_t)((ab * C::A_BYTES) >> 4);
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(b_full + stage, phase);
@@ -237,7 +249,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
             phase ^= 1;
           }
         }
-        if (leader) tc_commit(a_empty + kh);  // this K half may be refilled with the next band
+        if (leader) tc_commit(a_empty + ab);  // this array may be refilled
         __syncwarp();
       }
       if (leader) tc_commit(tmem_full_bar + slot);

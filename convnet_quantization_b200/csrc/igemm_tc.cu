@@ -418,6 +418,7 @@ extern "C" int b200q_conv3x3_tc(const uint8_t* x, uint8_t* y, int64_t b, const b
   if (!no_halo()) {
     int rc = 0;
     if (conv3x3_halo_dispatch(x, y, b, L, pool, s, &rc) == 0) return rc;
+    if (conv3x3_pair_dispatch(x, y, b, L, pool, s, &rc) == 0) return rc;
   }
 #define B200Q_TC_CASE(IMG_, CIN_, COUT_, RES_)                                                                  \
   if (L->img == IMG_ && L->cin == CIN_ && L->cout == COUT_) {                                                   \
