@@ -73,12 +73,14 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
   uint64_t* tmem_full_bar = empty_bar + 2;                  // [C1_SLOTS]
   uint64_t* tmem_empty_bar = tmem_full_bar + C1_SLOTS;      // [C1_SLOTS]
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + C1_SLOTS);
+  uint32_t* magic_smem = tmem_base_smem + 1;  // holds MAGIC_BITS (epilogue16.cuh epi_init)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t zp4 = (uint32_t)args.zp_x * 0x01010101u;
 
   if (warp == C1_PROD_WARP0 && lane == 0) {
+    *magic_smem = MAGIC_BITS;
     for (int i = 0; i < 2; ++i) {
       mbar_init(full_bar + i, C1_PROD_WARPS);
       mbar_init(empty_bar + i, 1);
@@ -226,7 +228,7 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
     const int ch0 = 16 * (lane & 3);
     const bool fast = args.bounded != 0;
     EpiRegs<16> K;
-    epi_init(consts, ch0, K);
+    epi_init(consts, ch0, magic_smem, K);
     static_assert(C1_TILES % C1_SETS == 0 && C1_SLOTS % C1_SETS == 0, "sets");
     for (int it = 0; it < my_imgs; ++it) {
       const int64_t img = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;

@@ -121,6 +121,7 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
   uint64_t* tmem_full_bar = w_bar + 1;                                     // [HALO_SLOTS]
   uint64_t* tmem_empty_bar = tmem_full_bar + HALO_SLOTS;                   // [HALO_SLOTS]
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + HALO_SLOTS);
+  uint32_t* magic_smem = tmem_base_smem + 1;  // holds MAGIC_BITS (epilogue16.cuh epi_init)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -137,6 +138,7 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
       mbar_init(tmem_empty_bar + i, 4 * C::PARTS);  // the warps of the one set that drains this slot
     }
     mbar_init(w_bar, 32);  // one cp.async-completion arrive per loader lane
+    *magic_smem = MAGIC_BITS;
     fence_barrier_init();
   }
   if (warp == HALO_MMA_WARP) {
@@ -278,7 +280,7 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
     const int ch0 = C::PARTW * part + C::NCH * (lane & 3);
     const bool fast = args.bounded != 0;
     EpiRegs<C::NCH> K;
-    epi_init(consts, ch0, K);
+    epi_init(consts, ch0, magic_smem, K);
     int acc_base = 0;
     for (int band = blockIdx.x; band < args.num_bands; band += gridDim.x, acc_base += C::TILES) {
       // first tile of this band that belongs to the set: acc_it = acc_base + t  with  acc_it % SETS == set

@@ -60,6 +60,8 @@ struct PairArgs {
   int64_t n_img;
   int num_bands;
   int zp_x, zp_out, lo, bounded;
+  int debug;  // B200Q_PAIR_DEBUG bits (timing experiments only; results are wrong when set): 2 = no MMAs, 4 = no
+              // activation copies, 8 = epilogue only drains, 32 = no weight TMA
 };
 
 struct alignas(16) PairConsts {  // the CTA's 128 output channels are [128*half, 128*half + 128)
@@ -96,6 +98,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   uint64_t* tmem_full_bar = b_empty + C::STAGES;            // [PAIR_SLOTS]
   uint64_t* tmem_empty_bar = tmem_full_bar + PAIR_SLOTS;    // [PAIR_SLOTS]
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + PAIR_SLOTS);
+  uint32_t* magic_smem = tmem_base_smem + 1;  // holds MAGIC_BITS (epilogue16.cuh epi_init)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -104,6 +107,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
 
   if (warp == PAIR_W_WARP && lane == 0) {
     tma_prefetch_desc(&map_w);
+    *magic_smem = MAGIC_BITS;
     for (int i = 0; i < NA; ++i) {
       mbar_init(a_full + i, 32);   // one cp.async-completion arrive per loader lane
       mbar_init(a_empty + i, 2);   // one commit per issuer
@@ -171,7 +175,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
         const uint32_t a_buf = smem_u32(a_smem + ab * C::A_BYTES);
         for (int bi = 0; bi < 2 * PAIR_T; ++bi) {
           const int64_t img = (int64_t)band * (2 * PAIR_T) + bi;
-          if (img >= args.n_img) break;  // stale data: those pixels are never stored
+          if (img >= args.n_img || (args.debug & 4)) break;  // stale data: those pixels are never stored
           const uint8_t* src = args.x + img * (int64_t)(IMG * IMG * CIN) + kh * C::KC + part * 16;
           const int pos0 = (bi >> 1) * C::PAIR_POS + (bi & 1) * (IMG + 1) + C::P + 1;  // pixel (0, 0)
 #pragma unroll
@@ -195,6 +199,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
         for (int j = 0; j < C::CHUNKS; ++j) {
           const int kh = j / 9, tap = j % 9;
           mbar_wait(b_empty + stage, phase ^ 1);
+          if (args.debug & 32) {
+            mbar_arrive(b_full + stage);
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_expect_tx(b_full + stage, C::B_BYTES);
           uint8_t* dst = b_smem + stage * C::B_BYTES;
           // dims (k, e, Q, b, u): channel = 16*Q + 4*u + 2*b + e; a box is one 64-channel part in epilogue row order
@@ -240,7 +252,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
             const uint64_t db0 = b_desc0 + (uint64_t)((stage * C::B_BYTES) >> 4);
 #pragma unroll
             for (int k = 0; k < C::MMAS_PER_CHUNK; ++k)
-              tc_mma_i8(d_tmem, da0 + (uint64_t)((k * 32) >> 4), db0 + (uint64_t)((k * 32) >> 4), idesc, 1u);
+              if (!(args.debug & 2)) tc_mma_i8(d_tmem, da0 + (uint64_t)((k * 32) >> 4), db0 + (uint64_t)((k * 32) >> 4), idesc, 1u);
             tc_commit(b_empty + stage);  // chunk reusable once both issuers' MMAs have read it
           }
           __syncwarp();
@@ -264,7 +276,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
     const int ch0 = PAIR_N * nhalf + ch_slot;                 // ... and within the layer
     const bool fast = args.bounded != 0;
     EpiRegs<PAIR_NCH> K;
-    epi_init(consts, ch0, K);
+    epi_init(consts, ch0, magic_smem, K);
     int acc_it = 0;
     for (int band = band0; band < args.num_bands; band += band_step) {
       for (int t = 0; t < PAIR_T; ++t, ++acc_it) {
@@ -276,6 +288,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
         };
         mbar_wait(tmem_full_bar + slot, (acc_it / PAIR_SLOTS) & 1);
         tc_fence_after();
+        if (args.debug & 8) {
+          tc_fence_before();
+          __syncwarp();
+          release();
+          continue;
+        }
         if constexpr (POOL) {
           // thread (j, q): pooled pixel (row = quarter, column j>>1) of image j&1
           const int64_t img = img0 + (j & 1);
@@ -335,7 +353,16 @@ static int launch_pair(const uint8_t* x, uint8_t* y, int64_t n_img, const b200q_
     attr_set = true;
   }
   const int num_bands = (int)((n_img + 2 * PAIR_T - 1) / (2 * PAIR_T));
-  PairArgs args{x, y, n_img, num_bands, L->zp_x, rq.zp_out, rq.relu ? rq.zp_out : 0, (rq.flags & B200Q_RQ_BOUNDED) ? 1 : 0};
+  static int debug = -1;
+  if (debug < 0) {
+    const char* e = getenv("B200Q_PAIR_DEBUG");
+    debug = e ? atoi(e) : 0;
+  }
+  PairArgs args{x,         y,
+                n_img,     num_bands,
+                L->zp_x,   rq.zp_out,
+                rq.relu ? rq.zp_out : 0, (rq.flags & B200Q_RQ_BOUNDED) ? 1 : 0,
+                debug};
   // two CTAs (one per channel half) per band; an even grid no larger than the SM count
   int grid = 2 * num_bands < num_sms() ? 2 * num_bands : (num_sms() & ~1);
   kernel<<<grid, PAIR_THREADS, C::SMEM_BYTES, stream>>>(map_w, consts, args);

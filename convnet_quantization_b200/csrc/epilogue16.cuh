@@ -45,9 +45,12 @@ struct EpiRegs {
   uint32_t fill[8];                 // MAGIC_BITS x 8 (operands of the re-arming tcgen05.st)
 };
 
-// ch0 = 4*NCH*part + NCH*(lane & 3)
+// ch0 = 4*NCH*part + NCH*(lane & 3).  magic_smem: a shared-memory word that holds MAGIC_BITS.  The fill registers are
+// read from it with volatile loads: ptxas otherwise treats them as constants and rebuilds all eight with MOVs in front
+// of every re-arming store (64 FMA-pipe instructions per block; declaring them read-write asm operands does not help,
+// ptxas knows tcgen05.st only reads them).
 template <int NCH, class Consts>
-__device__ __forceinline__ void epi_init(const Consts& c, int ch0, EpiRegs<NCH>& K) {
+__device__ __forceinline__ void epi_init(const Consts& c, int ch0, const uint32_t* magic_smem, EpiRegs<NCH>& K) {
 #pragma unroll
   for (int k = 0; k < NCH; ++k) {
     K.k1[k] = c.k1[ch0 + k];
@@ -55,7 +58,8 @@ __device__ __forceinline__ void epi_init(const Consts& c, int ch0, EpiRegs<NCH>&
     K.mu[k] = c.mult[ch0 + k];
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) K.fill[i] = MAGIC_BITS;
+  for (int i = 0; i < 8; ++i)
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(K.fill[i]) : "r"(smem_u32(magic_smem)) : "memory");
 }
 
 // 16 lanes x 8*REPS columns in the mma fragment layout: register r = 4i + 2s + e of thread t holds lane
@@ -89,12 +93,10 @@ __device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, uint32_t* v) {
         : "memory");
   }
 }
-// Re-arm 16 lanes x 16 columns with the pre-bias.  The fill registers are declared read-write so that the compiler
-// must keep them (as plain inputs it rebuilt all eight with MOVs in front of every store: 64 MOVs per block).
-__device__ __forceinline__ void tmem_st_fill_16x16(uint32_t taddr, uint32_t (&f)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
-               : "+r"(f[0]), "+r"(f[1]), "+r"(f[2]), "+r"(f[3]), "+r"(f[4]), "+r"(f[5]), "+r"(f[6]), "+r"(f[7])
-               : "r"(taddr)
+// Re-arm 16 lanes x 16 columns with the pre-bias.
+__device__ __forceinline__ void tmem_st_fill_16x16(uint32_t taddr, const uint32_t (&f)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(f[0]),
+               "r"(f[1]), "r"(f[2]), "r"(f[3]), "r"(f[4]), "r"(f[5]), "r"(f[6]), "r"(f[7])
                : "memory");
 }
 
