@@ -228,7 +228,7 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
     const int ch0 = 16 * (lane & 3);
     const bool fast = args.bounded != 0;
     EpiRegs<16> K;
-    epi_init(consts, ch0, magic_smem, K);
+    epi_init<16, /*PIN=*/false>(consts, ch0, magic_smem, K);
     static_assert(C1_TILES % C1_SETS == 0 && C1_SLOTS % C1_SETS == 0, "sets");
     for (int it = 0; it < my_imgs; ++it) {
       const int64_t img = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;

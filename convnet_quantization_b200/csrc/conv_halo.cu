@@ -281,35 +281,63 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
     const bool fast = args.bounded != 0;
     EpiRegs<C::NCH> K;
     epi_init(consts, ch0, magic_smem, K);
-    int acc_base = 0;
-    for (int band = blockIdx.x; band < args.num_bands; band += gridDim.x, acc_base += C::TILES) {
-      // first tile of this band that belongs to the set: acc_it = acc_base + t  with  acc_it % SETS == set
-      for (int t = (set - acc_base % C::SETS + C::SETS) % C::SETS; t < C::TILES; t += C::SETS) {
-        const int acc_it = acc_base + t;
-        const uint32_t slot = acc_it % HALO_SLOTS;
-        const int bi = t / (C::TILES_X * C::TILES_Y), tt = t % (C::TILES_X * C::TILES_Y);
-        const int r0 = (tt / C::TILES_X) * C::TILE_ROWS + 4 * quarter, c = (tt % C::TILES_X) * C::TILE_COLS + j;
-        const int64_t img = (int64_t)band * NBI + bi;
-        const bool valid = img < args.n_img;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * COUT + C::PARTW * part;
-        auto release = [&]() {
-          if (lane == 0) mbar_arrive(tmem_empty_bar + slot);
+    if constexpr (!POOL) {
+      if (!(args.debug & 8)) {
+        // software-pipelined over the warp's tiles (epilogue16.cuh epi_pipeline)
+        int band = blockIdx.x, acc_base = 0;
+        int t = (set - acc_base % C::SETS + C::SETS) % C::SETS;
+        auto next = [&](EpiTile& e) -> bool {
+          while (band < args.num_bands && t >= C::TILES) {
+            band += gridDim.x;
+            acc_base += C::TILES;
+            t = (set - acc_base % C::SETS + C::SETS) % C::SETS;
+          }
+          if (band >= args.num_bands) return false;
+          const int acc_it = acc_base + t;
+          const uint32_t slot = acc_it % HALO_SLOTS;
+          const int bi = t / (C::TILES_X * C::TILES_Y), tt = t % (C::TILES_X * C::TILES_Y);
+          const int r0 = (tt / C::TILES_X) * C::TILE_ROWS + 4 * quarter, c = (tt % C::TILES_X) * C::TILE_COLS + j;
+          const int64_t img = (int64_t)band * NBI + bi;
+          e.t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * COUT + C::PARTW * part;
+          e.full_bar = tmem_full_bar + slot;
+          e.empty_bar = tmem_empty_bar + slot;
+          e.parity = (acc_it / HALO_SLOTS) & 1;
+          e.out = args.y + ((img * IMG + r0) * IMG + c) * (int64_t)COUT + ch0;
+          e.valid0 = e.valid1 = img < args.n_img;
+          t += C::SETS;
+          return true;
         };
-        mbar_wait(tmem_full_bar + slot, (acc_it / HALO_SLOTS) & 1);
-        tc_fence_after();
-        if (args.debug & 8) {
-          tc_fence_before();
-          __syncwarp();
-          release();
-          continue;
-        }
-        if constexpr (POOL) {
-          uint8_t* out = args.y + ((img * (IMG / 2) + (r0 >> 1) + (j & 1)) * (IMG / 2) + (c >> 1)) * (int64_t)COUT + ch0;
-          epi_block_pool<CHECK>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, valid, lane, release);
-        } else {
-          uint8_t* out = args.y + ((img * IMG + r0) * IMG + c) * (int64_t)COUT + ch0;
-          epi_block<CHECK>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, (int64_t)IMG * COUT, 2 * (int64_t)IMG * COUT,
-                           valid, valid, release);
+        epi_pipeline<CHECK>(K, consts, ch0, fast, args.zp_out, args.lo, (int64_t)IMG * COUT, 2 * (int64_t)IMG * COUT, lane,
+                            next);
+      }
+    }
+    if (POOL || (args.debug & 8)) {
+      int acc_base = 0;
+      for (int band = blockIdx.x; band < args.num_bands; band += gridDim.x, acc_base += C::TILES) {
+        // first tile of this band that belongs to the set: acc_it = acc_base + t  with  acc_it % SETS == set
+        for (int t = (set - acc_base % C::SETS + C::SETS) % C::SETS; t < C::TILES; t += C::SETS) {
+          const int acc_it = acc_base + t;
+          const uint32_t slot = acc_it % HALO_SLOTS;
+          const int bi = t / (C::TILES_X * C::TILES_Y), tt = t % (C::TILES_X * C::TILES_Y);
+          const int r0 = (tt / C::TILES_X) * C::TILE_ROWS + 4 * quarter, c = (tt % C::TILES_X) * C::TILE_COLS + j;
+          const int64_t img = (int64_t)band * NBI + bi;
+          const bool valid = img < args.n_img;
+          const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * COUT + C::PARTW * part;
+          auto release = [&]() {
+            if (lane == 0) mbar_arrive(tmem_empty_bar + slot);
+          };
+          mbar_wait(tmem_full_bar + slot, (acc_it / HALO_SLOTS) & 1);
+          tc_fence_after();
+          if (args.debug & 8) {
+            tc_fence_before();
+            __syncwarp();
+            release();
+            continue;
+          }
+          if constexpr (POOL) {
+            uint8_t* out = args.y + ((img * (IMG / 2) + (r0 >> 1) + (j & 1)) * (IMG / 2) + (c >> 1)) * (int64_t)COUT + ch0;
+            epi_block_pool<CHECK>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, valid, lane, release);
+          }  // (!POOL reaches this loop only in the drain-only timing mode)
         }
       }
     }

@@ -277,35 +277,59 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
     const bool fast = args.bounded != 0;
     EpiRegs<PAIR_NCH> K;
     epi_init(consts, ch0, magic_smem, K);
-    int acc_it = 0;
-    for (int band = band0; band < args.num_bands; band += band_step) {
-      for (int t = 0; t < PAIR_T; ++t, ++acc_it) {
-        const uint32_t slot = acc_it % PAIR_SLOTS;
-        const int64_t img0 = (int64_t)band * (2 * PAIR_T) + 2 * t;   // image 0 of the pair
-        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * PAIR_N + 64 * part;
-        auto release = [&]() {
-          if (lane == 0) mbar_arrive(tmem_empty_bar + slot);
+    if constexpr (!POOL) {
+      if (!(args.debug & 8)) {
+        // software-pipelined over the warp's tiles (epilogue16.cuh epi_pipeline); accumulator row 16*half + 8*s + j of
+        // the quarter = pixel (2*quarter + half, j) of image s of the pair
+        int band = band0, t = 0, acc_it = 0;
+        auto next = [&](EpiTile& e) -> bool {
+          if (t == PAIR_T) {
+            t = 0;
+            band += band_step;
+          }
+          if (band >= args.num_bands) return false;
+          const uint32_t slot = acc_it % PAIR_SLOTS;
+          const int64_t img0 = (int64_t)band * (2 * PAIR_T) + 2 * t;
+          e.t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * PAIR_N + 64 * part;
+          e.full_bar = tmem_full_bar + slot;
+          e.empty_bar = tmem_empty_bar + slot;
+          e.parity = (acc_it / PAIR_SLOTS) & 1;
+          e.out = args.y + ((img0 * IMG + 2 * quarter) * IMG + j) * (int64_t)COUT + ch0;
+          e.valid0 = img0 < args.n_img;
+          e.valid1 = img0 + 1 < args.n_img;
+          ++t;
+          ++acc_it;
+          return true;
         };
-        mbar_wait(tmem_full_bar + slot, (acc_it / PAIR_SLOTS) & 1);
-        tc_fence_after();
-        if (args.debug & 8) {
-          tc_fence_before();
-          __syncwarp();
-          release();
-          continue;
-        }
-        if constexpr (POOL) {
-          // thread (j, q): pooled pixel (row = quarter, column j>>1) of image j&1
-          const int64_t img = img0 + (j & 1);
-          uint8_t* out = args.y + ((img * (IMG / 2) + quarter) * (IMG / 2) + (j >> 1)) * (int64_t)COUT + ch0;
-          epi_block_pool<CHECK, PAIR_NCH, /*PAIRED=*/true>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out,
-                                                          img < args.n_img, lane, release);
-        } else {
-          // accumulator row 16*half + 8*s + j of the quarter = pixel (2*quarter + half, j) of image s
-          uint8_t* out = args.y + ((img0 * IMG + 2 * quarter) * IMG + j) * (int64_t)COUT + ch0;
-          epi_block<CHECK, PAIR_NCH>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out,
-                                     (int64_t)IMG * IMG * COUT, (int64_t)IMG * COUT, img0 < args.n_img,
-                                     img0 + 1 < args.n_img, release);
+        epi_pipeline<CHECK>(K, consts, ch0, fast, args.zp_out, args.lo, (int64_t)IMG * IMG * COUT, (int64_t)IMG * COUT, lane,
+                            next);
+      }
+    }
+    if (POOL || (args.debug & 8)) {
+      int acc_it = 0;
+      for (int band = band0; band < args.num_bands; band += band_step) {
+        for (int t = 0; t < PAIR_T; ++t, ++acc_it) {
+          const uint32_t slot = acc_it % PAIR_SLOTS;
+          const int64_t img0 = (int64_t)band * (2 * PAIR_T) + 2 * t;   // image 0 of the pair
+          const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * PAIR_N + 64 * part;
+          auto release = [&]() {
+            if (lane == 0) mbar_arrive(tmem_empty_bar + slot);
+          };
+          mbar_wait(tmem_full_bar + slot, (acc_it / PAIR_SLOTS) & 1);
+          tc_fence_after();
+          if (args.debug & 8) {
+            tc_fence_before();
+            __syncwarp();
+            release();
+            continue;
+          }
+          if constexpr (POOL) {
+            // thread (j, q): pooled pixel (row = quarter, column j>>1) of image j&1
+            const int64_t img = img0 + (j & 1);
+            uint8_t* out = args.y + ((img * (IMG / 2) + quarter) * (IMG / 2) + (j >> 1)) * (int64_t)COUT + ch0;
+            epi_block_pool<CHECK, PAIR_NCH, /*PAIRED=*/true>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out,
+                                                            img < args.n_img, lane, release);
+          }  // (!POOL reaches this loop only in the drain-only timing mode)
         }
       }
     }

@@ -49,13 +49,19 @@ struct EpiRegs {
 // read from it with volatile loads: ptxas otherwise treats them as constants and rebuilds all eight with MOVs in front
 // of every re-arming store (64 FMA-pipe instructions per block; declaring them read-write asm operands does not help,
 // ptxas knows tcgen05.st only reads them).
-template <int NCH, class Consts>
+template <int NCH, bool PIN = true, class Consts>
 __device__ __forceinline__ void epi_init(const Consts& c, int ch0, const uint32_t* magic_smem, EpiRegs<NCH>& K) {
+  // The constants pass through a self-shuffle for the same reason: under register pressure ptxas does not spill them
+  // but RE-LOADS them with register-indexed LDC in the middle of the arithmetic, and those go through the
+  // address-divergence pipe that tcgen05.ld/st and the mbarrier instructions need (measured: that pipe 89 % busy,
+  // kernel 1.8x slower).  A shuffle result cannot be rematerialised.  PIN = false leaves the choice to ptxas (conv1,
+  // whose 13 warps leave 128 registers: pinning all 48 constants there costs more than the occasional re-load).
+  const int self = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < NCH; ++k) {
-    K.k1[k] = c.k1[ch0 + k];
-    K.bd[k] = c.bdiv[ch0 + k];
-    K.mu[k] = c.mult[ch0 + k];
+    K.k1[k] = PIN ? __shfl_sync(0xffffffffu, c.k1[ch0 + k], self) : c.k1[ch0 + k];
+    K.bd[k] = PIN ? __shfl_sync(0xffffffffu, c.bdiv[ch0 + k], self) : c.bdiv[ch0 + k];
+    K.mu[k] = PIN ? __shfl_sync(0xffffffffu, c.mult[ch0 + k], self) : c.mult[ch0 + k];
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -206,6 +212,89 @@ __device__ __forceinline__ void epi_block(uint32_t t_addr, EpiRegs<NCH>& K, cons
       }
       if (s == 0 ? valid0 : valid1) epi_store<G>(out + half * stride_half + s * stride_s, packed);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------ no pooling, software-pipelined
+// The un-pooled layers (conv3, conv5; conv1) requantise every accumulator and are bound by their epilogue warps, which
+// with one block at a time idle through a TMEM round trip per block (both warps of a scheduler wait, read, compute and
+// store in lock-step).  Here a warp keeps one 16-lane half in flight while it computes the other: the tcgen05.ld of
+// half 1 is issued before the arithmetic of half 0, and the first half of the NEXT tile before the arithmetic of
+// half 1.  `next(EpiTile&)` yields the warp's tiles in order (false when there are none left).
+struct EpiTile {
+  uint32_t t_addr;        // tmem base + (quarter*32 << 16) + first column of the warp's part
+  uint64_t* full_bar;     // accumulator complete (MMA commit)
+  uint64_t* empty_bar;    // slot drained (one arrive per epilogue warp)
+  uint32_t parity;        // phase parity of full_bar for this tile
+  uint8_t* out;           // see epi_block
+  bool valid0, valid1;
+};
+
+template <bool CHECK, int NCH, class Consts>
+__device__ __forceinline__ void epi_half(const uint32_t (&v)[2 * NCH], const EpiRegs<NCH>& K, const Consts& consts, int ch0,
+                                         bool fast, int zp_out, int lo, uint8_t* out, int64_t stride_s, bool valid0,
+                                         bool valid1) {
+  constexpr int G = NCH / 4;
+  const int zp_sub = zp_out - (int)MAGIC_BITS;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    uint32_t packed[G];
+    uint32_t bad = 0;
+    if (fast) {
+      const uint32_t* w = v + 2 * s;
+      packed[0] = epi_requant4<CHECK, 0>(w[0], w[1], w[4], w[5], K, zp_sub, lo, bad);
+      packed[1] = epi_requant4<CHECK, 4>(w[8], w[9], w[12], w[13], K, zp_sub, lo, bad);
+      if constexpr (G == 4) {
+        packed[2] = epi_requant4<CHECK, 8>(w[16], w[17], w[20], w[21], K, zp_sub, lo, bad);
+        packed[3] = epi_requant4<CHECK, 12>(w[24], w[25], w[28], w[29], K, zp_sub, lo, bad);
+      }
+    }
+    if (!fast || (CHECK && __any_sync(0xffffffffu, requant_magic_out_of_range(bad)))) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const uint32_t* w = v + 8 * g + 2 * s;
+        packed[g] = epi_requant4_exact(w[0], w[1], w[4], w[5], consts, ch0 + 4 * g, zp_out, lo);
+      }
+    }
+    if (s == 0 ? valid0 : valid1) epi_store<G>(out + s * stride_s, packed);
+  }
+}
+
+template <bool CHECK, int NCH, class Consts, class Next>
+__device__ __forceinline__ void epi_pipeline(EpiRegs<NCH>& K, const Consts& consts, int ch0, bool fast, int zp_out, int lo,
+                                             int64_t stride_s, int64_t stride_half, int lane, Next next) {
+  constexpr int PARTW = 4 * NCH;
+  constexpr uint32_t HALF1 = 16u << 16;
+  EpiTile cur;
+  bool have = next(cur);
+  if (!have) return;
+  uint32_t v0[2 * NCH], v1[2 * NCH];
+  mbar_wait(cur.full_bar, cur.parity);
+  tc_fence_after();
+  tmem_ld_frag<PARTW / 8>(cur.t_addr, v0);
+  while (have) {
+    tmem_ld_wait();                                     // half 0 has landed
+    tmem_ld_frag<PARTW / 8>(cur.t_addr + HALF1, v1);    // half 1 in flight during the arithmetic of half 0
+#pragma unroll
+    for (int c = 0; c < PARTW; c += 16) tmem_st_fill_16x16(cur.t_addr + c, K.fill);
+    epi_half<CHECK>(v0, K, consts, ch0, fast, zp_out, lo, cur.out, stride_s, cur.valid0, cur.valid1);
+    tmem_ld_wait();                                     // half 1 has landed
+#pragma unroll
+    for (int c = 0; c < PARTW; c += 16) tmem_st_fill_16x16(cur.t_addr + HALF1 + c, K.fill);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(cur.empty_bar);          // slot read and re-armed: back to the MMA issuer
+    EpiTile nxt;
+    const bool have_next = next(nxt);
+    if (have_next) {                                    // first half of the next tile in flight during half 1
+      mbar_wait(nxt.full_bar, nxt.parity);
+      tc_fence_after();
+      tmem_ld_frag<PARTW / 8>(nxt.t_addr, v0);
+    }
+    epi_half<CHECK>(v1, K, consts, ch0, fast, zp_out, lo, cur.out + stride_half, stride_s, cur.valid0, cur.valid1);
+    cur = nxt;
+    have = have_next;
   }
 }
 

@@ -9,6 +9,8 @@ calls ``eval()/cpu()/model(cpu_images)`` and ``outputs.topk`` on the result):
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -72,7 +74,10 @@ class B200StaticQuantizedNet(_GpuResident):
     ``device='cpu'``) are processed in chunks on two CUDA streams, so the host->device copy of chunk i+1 overlaps
     the kernels of chunk i; logits come back through a pinned staging buffer."""
 
-    HOST_CHUNK = 4096  # images per pipelined chunk (48 MiB of fp32 input)
+    # images per pipelined chunk (B200Q_HOST_CHUNK overrides, for tuning).  The pipeline is bound by the host->device
+    # copy (12 KiB of fp32 per image over PCIe), so what the chunk size controls is the un-overlapped tail: the kernels
+    # of the LAST chunk.  2048 images = 24 MiB per copy, still far above the size where PCIe copies lose efficiency.
+    HOST_CHUNK = int(os.environ.get("B200Q_HOST_CHUNK", "2048"))
 
     def __init__(self, qparams: dict, device=None):
         super().__init__(device)
