@@ -273,18 +273,19 @@ __device__ __forceinline__ void epi_pipeline(EpiRegs<NCH>& K, const Consts& cons
   tc_fence_after();
   tmem_ld_frag<PARTW / 8>(cur.t_addr, v0);
   while (have) {
+    // TMEM loads and stores of a warp are served in order: a store issued right behind a load stalls the warp until
+    // the load has been served, and tcgen05.wait::st exposes the store latency.  So every re-arming store is issued
+    // when no load is in flight, and the slot is handed back after the arithmetic of half 1 (four slots: the issuer
+    // needs it three tiles later).
     tmem_ld_wait();                                     // half 0 has landed
     tmem_ld_frag<PARTW / 8>(cur.t_addr + HALF1, v1);    // half 1 in flight during the arithmetic of half 0
-#pragma unroll
-    for (int c = 0; c < PARTW; c += 16) tmem_st_fill_16x16(cur.t_addr + c, K.fill);
     epi_half<CHECK>(v0, K, consts, ch0, fast, zp_out, lo, cur.out, stride_s, cur.valid0, cur.valid1);
     tmem_ld_wait();                                     // half 1 has landed
 #pragma unroll
-    for (int c = 0; c < PARTW; c += 16) tmem_st_fill_16x16(cur.t_addr + HALF1 + c, K.fill);
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(cur.empty_bar);          // slot read and re-armed: back to the MMA issuer
+    for (int c = 0; c < PARTW; c += 16) {
+      tmem_st_fill_16x16(cur.t_addr + c, K.fill);
+      tmem_st_fill_16x16(cur.t_addr + HALF1 + c, K.fill);
+    }
     EpiTile nxt;
     const bool have_next = next(nxt);
     if (have_next) {                                    // first half of the next tile in flight during half 1
@@ -293,6 +294,10 @@ __device__ __forceinline__ void epi_pipeline(EpiRegs<NCH>& K, const Consts& cons
       tmem_ld_frag<PARTW / 8>(nxt.t_addr, v0);
     }
     epi_half<CHECK>(v1, K, consts, ch0, fast, zp_out, lo, cur.out + stride_half, stride_s, cur.valid0, cur.valid1);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(cur.empty_bar);          // slot read and re-armed: back to the MMA issuer
     cur = nxt;
     have = have_next;
   }
