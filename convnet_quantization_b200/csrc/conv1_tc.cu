@@ -7,9 +7,12 @@
 // requantised channels per pixel) and by the 77.8 KB/image it moves through HBM.  What the CUDA-core version
 // (simt.cu) spent on 576 dp4a + 128 conversion-pipe instructions per pixel is gone.
 //
-// Roles (416 threads): warps 0..7 epilogue (epilogue16.cuh, same scheme as conv_halo.cu: 8x16-pixel block tiles, four
-// TMEM slots, pre-biased accumulators, two sets of four warps taking alternate tiles), warps 8..11 producers, warp 12
-// MMA issuer.  13 warps leave 128 registers per thread, which the register-resident epilogue constants need.
+// Roles (384 threads): warps 0..7 epilogue (epilogue16.cuh, same scheme as conv_halo.cu: 8x16-pixel block tiles,
+// pre-biased accumulators, two sets of four warps taking alternate tiles, software-pipelined over the tiles), warps
+// 8..11 producers.  There is no MMA warp: the first producer warp issues the image's eight MMAs right after the im2col
+// rows are complete, so the CTA has 12 warps = 3 per scheduler and 168 registers per thread, which the pipelined
+// epilogue (two accumulator halves + 48 constants in registers) needs.  The eight TMEM slots hold one whole image
+// (slot = tile), so that warp only ever waits for the epilogue of the previous image.
 // Producers, per image: (1) quantise the fp32 planes (exact aten arithmetic, without the conversion pipe) into a
 // padded 34x34 image of {c0,c1,c2,zp} words whose border holds the zero-point; (2) gather the im2col rows
 // [pixel][tap*3+ch] (27 bytes + 5 zero bytes) with byte permutes and store them tile-major in the 32-byte-swizzled
@@ -24,9 +27,9 @@ namespace b200q {
 
 constexpr int C1_EPI_WARPS = 8, C1_PROD_WARPS = 4;
 constexpr int C1_SETS = C1_EPI_WARPS / 4;
-constexpr int C1_PROD_WARP0 = C1_EPI_WARPS, C1_MMA_WARP = C1_EPI_WARPS + C1_PROD_WARPS;
-constexpr int C1_THREADS = 32 * (C1_EPI_WARPS + C1_PROD_WARPS + 1);
-constexpr int C1_SLOTS = 4;
+constexpr int C1_PROD_WARP0 = C1_EPI_WARPS;
+constexpr int C1_THREADS = 32 * (C1_EPI_WARPS + C1_PROD_WARPS);
+constexpr int C1_SLOTS = 8;
 constexpr int C1_IMG = 32, C1_COUT = 64, C1_KB = 32;       // K bytes per row
 constexpr int C1_TILES = 8;                                  // 2 x 4 blocks of 16 rows x 8 columns
 constexpr int C1_A_TILE = 128 * C1_KB, C1_A_BYTES = C1_TILES * C1_A_TILE;  // 4 KB, 32 KB
@@ -68,8 +71,7 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
   uint8_t* a_smem = smem;                                   // [2][8 tiles][128 rows][32 B]
   uint8_t* b_smem = a_smem + 2 * C1_A_BYTES;                // [64][32 B]
   uint32_t* q_img = reinterpret_cast<uint32_t*>(b_smem + C1_B_BYTES);  // [34][34] words {c0,c1,c2,zp}
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(q_img) + C1_Q_BYTES);  // [2]
-  uint64_t* empty_bar = full_bar + 2;                       // [2]
+  uint64_t* empty_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(q_img) + C1_Q_BYTES);  // [2]
   uint64_t* tmem_full_bar = empty_bar + 2;                  // [C1_SLOTS]
   uint64_t* tmem_empty_bar = tmem_full_bar + C1_SLOTS;      // [C1_SLOTS]
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + C1_SLOTS);
@@ -81,17 +83,14 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
 
   if (warp == C1_PROD_WARP0 && lane == 0) {
     *magic_smem = MAGIC_BITS;
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(full_bar + i, C1_PROD_WARPS);
-      mbar_init(empty_bar + i, 1);
-    }
+    for (int i = 0; i < 2; ++i) mbar_init(empty_bar + i, 1);
     for (int i = 0; i < C1_SLOTS; ++i) {
       mbar_init(tmem_full_bar + i, 1);
-      mbar_init(tmem_empty_bar + i, 4);  // the four warps of the set that drains this slot
+      mbar_init(tmem_empty_bar + i, 4);  // the four warps of the set that drains this slot (slot = tile)
     }
     fence_barrier_init();
   }
-  if (warp == C1_MMA_WARP) {
+  if (warp == C1_PROD_WARP0) {
     tmem_alloc(tmem_base_smem, C1_SLOTS * C1_COUT);
     tmem_relinquish();
   }
@@ -134,11 +133,14 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
 
   const int my_imgs = ((int64_t)blockIdx.x < args.n_img) ? (int)((args.n_img - 1 - blockIdx.x) / gridDim.x + 1) : 0;
 
-  if (warp >= C1_PROD_WARP0 && warp < C1_MMA_WARP) {
+  if (warp >= C1_PROD_WARP0) {
     // ================================================================== producers (128 threads)
     const int p = threadIdx.x - 32 * C1_PROD_WARP0;
     const int zp_sub = args.zp_x - (int)MAGIC_BITS;
     const uint32_t zp_hi = (uint32_t)args.zp_x << 24;
+    const bool leader = elect_one() != 0;
+    constexpr uint32_t idesc = make_idesc_i8(128, C1_COUT);
+    const uint64_t b_desc = make_kmajor_desc<C1_KB>(smem_u32(b_smem), 8 * C1_KB);
     // thread p owns image row p/4, columns 8*(p%4) .. +7 of the fp32 planes.  The loads of image it+1 are issued right
     // after image it has been quantised, so their HBM latency overlaps the im2col pass and the barrier waits.
     const int row = p >> 2, col0 = (p & 3) * 8;
@@ -191,67 +193,60 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
         *reinterpret_cast<uint4*>(rowp + (sw << 4)) = lo4;
         *reinterpret_cast<uint4*>(rowp + ((sw ^ 1) << 4)) = hi4;
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar + buf);
-      asm volatile("bar.sync 2, %0;" ::"n"(32 * C1_PROD_WARPS) : "memory");  // q_img free for the next image
-    }
-  } else if (warp == C1_MMA_WARP) {
-    // ================================================================== MMA issuer: one MMA per tile
-    const bool leader = elect_one() != 0;
-    constexpr uint32_t idesc = make_idesc_i8(128, C1_COUT);
-    const uint64_t b_desc = make_kmajor_desc<C1_KB>(smem_u32(b_smem), 8 * C1_KB);
-    int acc_it = 0;
-    for (int it = 0; it < my_imgs; ++it) {
-      const int buf = it & 1;
-      mbar_wait(full_bar + buf, (it >> 1) & 1);
-      tc_fence_after();
-      const uint64_t a_desc0 = make_kmajor_desc<C1_KB>(smem_u32(a_smem + buf * C1_A_BYTES), 8 * C1_KB);
-      for (int t = 0; t < C1_TILES; ++t, ++acc_it) {
-        const uint32_t slot = acc_it % C1_SLOTS;
-        mbar_wait(tmem_empty_bar + slot, ((acc_it / C1_SLOTS) & 1) ^ 1);
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * C1_PROD_WARPS) : "memory");  // a_buf complete; q_img free again
+      // ---- (3) the first producer warp issues the image's MMAs: one per tile, slot = tile
+      if (warp == C1_PROD_WARP0) {
         tc_fence_after();
-        if (leader) {
-          tc_mma_i8(tmem_base + slot * C1_COUT, a_desc0 + (uint64_t)((t * C1_A_TILE) >> 4), b_desc, idesc, 1u);
-          tc_commit(tmem_full_bar + slot);
+        const uint64_t a_desc0 = make_kmajor_desc<C1_KB>(smem_u32(a_buf), 8 * C1_KB);
+        for (int t = 0; t < C1_TILES; ++t) {
+          mbar_wait(tmem_empty_bar + t, (it & 1) ^ 1);  // drained by the epilogue of the previous image
+          tc_fence_after();
+          if (leader) {
+            tc_mma_i8(tmem_base + t * C1_COUT, a_desc0 + (uint64_t)((t * C1_A_TILE) >> 4), b_desc, idesc, 1u);
+            tc_commit(tmem_full_bar + t);
+          }
+          __syncwarp();
         }
+        if (leader) tc_commit(empty_bar + buf);  // a_buf reusable once these MMAs have read it
         __syncwarp();
       }
-      if (leader) tc_commit(empty_bar + buf);
-      __syncwarp();
     }
   } else {
     // ================================================================== epilogue warps (independent of each other)
+    static_assert(C1_SLOTS == C1_TILES && C1_TILES % C1_SETS == 0, "slot = tile of the image");
     const int quarter = warp & 3;
-    const int set = warp >> 2;                 // takes the tiles with acc_it % C1_SETS == set
+    const int set = warp >> 2;                 // takes the tiles t with t % C1_SETS == set
     const int j = lane >> 2;                   // column of the 8-column block
     const int ch0 = 16 * (lane & 3);
     const bool fast = args.bounded != 0;
     EpiRegs<16> K;
-    epi_init<16, /*PIN=*/false>(consts, ch0, magic_smem, K);
-    static_assert(C1_TILES % C1_SETS == 0 && C1_SLOTS % C1_SETS == 0, "sets");
-    for (int it = 0; it < my_imgs; ++it) {
-      const int64_t img = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
-      for (int t = set; t < C1_TILES; t += C1_SETS) {
-        const int acc_it = it * C1_TILES + t;
-        const uint32_t slot = acc_it % C1_SLOTS;
-        const int r0 = (t >> 2) * 16 + 4 * quarter, c = (t & 3) * 8 + j;
-        uint8_t* out = args.y + ((img * C1_IMG + r0) * C1_IMG + c) * (int64_t)C1_COUT + ch0;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * C1_COUT;
-        auto release = [&]() {
-          if (lane == 0) mbar_arrive(tmem_empty_bar + slot);
-        };
-        mbar_wait(tmem_full_bar + slot, (acc_it / C1_SLOTS) & 1);
-        tc_fence_after();
-        epi_block<CHECK, 16, /*SPLIT=*/true>(t_addr, K, consts, ch0, fast, args.zp_out, args.lo, out, (int64_t)C1_IMG * C1_COUT,
-                                             2 * (int64_t)C1_IMG * C1_COUT, true, true, release);
+    epi_init(consts, ch0, magic_smem, K);
+    int it = 0, t = set;
+    auto next = [&](EpiTile& e) -> bool {
+      if (t >= C1_TILES) {
+        t = set;
+        ++it;
       }
-    }
+      if (it >= my_imgs) return false;
+      const int64_t img = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+      const int r0 = (t >> 2) * 16 + 4 * quarter, c = (t & 3) * 8 + j;
+      e.t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * C1_COUT;
+      e.full_bar = tmem_full_bar + t;
+      e.empty_bar = tmem_empty_bar + t;
+      e.parity = it & 1;
+      e.out = args.y + ((img * C1_IMG + r0) * C1_IMG + c) * (int64_t)C1_COUT + ch0;
+      e.valid0 = e.valid1 = true;
+      t += C1_SETS;
+      return true;
+    };
+    epi_pipeline<CHECK>(K, consts, ch0, fast, args.zp_out, args.lo, (int64_t)C1_IMG * C1_COUT, 2 * (int64_t)C1_IMG * C1_COUT,
+                        lane, next);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == C1_MMA_WARP) {
+  if (warp == C1_PROD_WARP0) {
     __syncwarp();
     tmem_dealloc(tmem_base, C1_SLOTS * C1_COUT);
   }
