@@ -78,6 +78,7 @@ class B200StaticQuantizedNet(_GpuResident):
     # copy (12 KiB of fp32 per image over PCIe), so what the chunk size controls is the un-overlapped tail: the kernels
     # of the LAST chunk.  2048 images = 24 MiB per copy, still far above the size where PCIe copies lose efficiency.
     HOST_CHUNK = int(os.environ.get("B200Q_HOST_CHUNK", "2048"))
+    TAIL_MIN = int(os.environ.get("B200Q_TAIL_MIN", "256"))
 
     def __init__(self, qparams: dict, device=None):
         super().__init__(device)
@@ -101,6 +102,22 @@ class B200StaticQuantizedNet(_GpuResident):
             }
         return self._pipe
 
+    def _chunks(self, b: int):
+        """(offset, size) of the pipelined chunks.  The copies run back to back, so the un-overlapped part of a call is
+        the kernels of the LAST chunk; the final ``HOST_CHUNK`` images are therefore split 3/4 + 1/4 (one extra chunk:
+        every chunk costs ~30 us of fixed overhead, and chunks much smaller than 512 images take longer to compute than
+        to copy - measured, scripts/gpu_e2e_chunks.sh)."""
+        lo = 0
+        while b - lo > self.HOST_CHUNK:
+            yield lo, self.HOST_CHUNK
+            lo += self.HOST_CHUNK
+        rest = b - lo
+        tail = rest // 4
+        if tail >= self.TAIL_MIN:
+            yield lo, rest - tail
+            lo += rest - tail
+        yield lo, b - lo
+
     def _forward_host(self, x: torch.Tensor) -> torch.Tensor:
         b = x.shape[0]
         x = x.contiguous()
@@ -111,8 +128,7 @@ class B200StaticQuantizedNet(_GpuResident):
         cur = torch.cuda.current_stream(self.engine_device)
         for s in pipe["streams"]:
             s.wait_stream(cur)
-        for i, lo in enumerate(range(0, b, self.HOST_CHUNK)):
-            n = min(self.HOST_CHUNK, b - lo)
+        for i, (lo, n) in enumerate(self._chunks(b)):
             k = i & 1
             with torch.cuda.stream(pipe["streams"][k]):  # per-stream buffers: reuse is ordered by the stream itself
                 xin, yout = pipe["x"][k][:n], pipe["y"][k][:n]
