@@ -228,6 +228,43 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(const LinearArgs a) {
   }
 }
 
+// Narrow head (fc2: k = 512, n = 10) fused with aten::dequantize.  The generic tile kernel above pads n to 64 and ran
+// this 8 MB layer at 29 us; here a warp owns one image at a time: lane l reads bytes [16l, 16l+16) of the image's row
+// (one coalesced 512-byte load per image), holds the matching 16 bytes of all N weight rows in registers, and the N
+// dot products are completed with the warp-reduce instruction.  Lane n then requantises and dequantises output n.
+template <int N>
+__global__ void __launch_bounds__(256) linear_head_dequant_kernel(const LinearArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  uint4 w[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) w[n] = __ldg(reinterpret_cast<const uint4*>(a.w + (int64_t)n * 512) + lane);
+  const int nn = lane < N ? lane : 0;
+  const int corr = __ldg(a.corr + nn);
+  const float bdiv = __ldg(a.bdiv + nn), mult = __ldg(a.mult + nn);
+  const int lo = a.relu ? a.zp_out : 0;
+  uint4 xv = make_uint4(0, 0, 0, 0);
+  if (warp < a.b) xv = __ldg(reinterpret_cast<const uint4*>(a.x + (int64_t)warp * 512) + lane);
+  for (int64_t img = warp; img < a.b; img += nwarps) {
+    const uint4 x = xv;
+    if (img + nwarps < a.b) xv = __ldg(reinterpret_cast<const uint4*>(a.x + (img + nwarps) * 512) + lane);  // prefetch
+    int mine = 0;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      int acc = dp4a_us(x.x, w[n].x, 0);
+      acc = dp4a_us(x.y, w[n].y, acc);
+      acc = dp4a_us(x.z, w[n].z, acc);
+      acc = dp4a_us(x.w, w[n].w, acc);
+      acc = __reduce_add_sync(0xffffffffu, acc);
+      if (lane == n) mine = acc;
+    }
+    if (lane < N) {
+      const uint32_t q = requant_u8(mine - corr, bdiv, mult, a.zp_out, lo);
+      reinterpret_cast<float*>(a.y)[img * N + lane] = __fmul_rn(__int2float_rn((int)q - a.zp_out), a.out_scale);
+    }
+  }
+}
+
 template <int EPI>
 static int launch_linear(const LinearArgs& a, cudaStream_t s) {
   dim3 grid((unsigned)((a.b + 63) / 64), (unsigned)((a.n + 63) / 64));
@@ -322,6 +359,11 @@ extern "C" int b200q_linear_dequant(const uint8_t* x, float* y, int64_t b, const
   if (b == 0) return 0;
   LinearArgs a{x, y, L->w, L->corr, L->rq.mult, L->rq.bdiv, nullptr, b, L->k, L->n, L->rq.zp_out, L->rq.relu,
                out_scale};
+  if (L->k == 512 && L->n == 10 && (uintptr_t)x % 16 == 0 && (uintptr_t)L->w % 16 == 0) {
+    const int64_t warps = b < (int64_t)num_sms() * 64 ? b : (int64_t)num_sms() * 64;  // <= 8 blocks of 8 warps per SM
+    linear_head_dequant_kernel<10><<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(a);
+    return launched("linear_head_dequant_kernel");
+  }
   return launch_linear<EPI_REQUANT_DEQUANT_F32>(a, (cudaStream_t)stream);
 }
 

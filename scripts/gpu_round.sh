@@ -12,5 +12,5 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 echo "ncu launches exit=$?"
 # ncu --set full of the 8 kernels of one forward at the bench batch (after the same command ran plain)
 timeout 300 python scripts/prof_net.py > gpurun_out/prof_net_plain.log 2>&1 &&
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'conv1_tc|conv_halo|conv_pair|igemm_tc|linear_simt|linear_dequant' -s 16 -c 8 -f -o gpurun_out/prof_net python scripts/prof_net.py > gpurun_out/prof_net_ncu.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'conv1_tc|conv_halo|conv_pair|igemm_tc|linear_simt|linear_head' -s 16 -c 8 -f -o gpurun_out/prof_net python scripts/prof_net.py > gpurun_out/prof_net_ncu.log 2>&1
 echo "ncu net exit=$? :: $(tail -n 1 gpurun_out/prof_net_ncu.log)"
