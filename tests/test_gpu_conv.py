@@ -152,9 +152,10 @@ def _stress_layer(name, qparams, huge):
     return L
 
 
-@pytest.mark.parametrize("name", ["conv2", "conv6"])
+@pytest.mark.parametrize("name", ["conv2", "conv3", "conv6"])
 @pytest.mark.parametrize("mode", ["huge_acc", "big_mult"])
-def test_conv_tc_requant_fallback_paths(qparams, name, mode):
+@pytest.mark.parametrize("pool", [False, True])
+def test_conv_tc_requant_fallback_paths(qparams, name, mode, pool):
     """The conversion-free epilogue must hand over to the exact I2F/F2I form (run-time range test, or the BOUNDED flag
     withheld at pack time) and stay bit-exact: accumulators up to ~7e7 and multipliers > 0.5."""
     from convnet_quantization_b200 import _lib, ops
@@ -181,8 +182,13 @@ def test_conv_tc_requant_fallback_paths(qparams, name, mode):
     x[0] = 255   # one saturated image: every accumulator of it is at the extreme
     x[1, : pc.img // 2] = 0
     Lnp = qparams_to_numpy({"l": L})["l"]
+    if pool and name == "conv3":
+        pytest.skip("conv3 is never pooled in the net; its pooled geometry is not instantiated")
+    from oracle import int_ops as IO
     want = _want_conv(x.numpy(), s, zp, Lnp)
-    got = ops.conv2d_q(x.cuda(), pc, impl="tc")
+    if pool:  # fused 2x2 max-pool: pooling runs on the raw accumulators, BEFORE either requantisation form
+        want = IO.max_pool2x2(want)
+    got = ops.conv2d_q(x.cuda(), pc, pool2x2=pool, impl="tc")
     torch.cuda.synchronize()
     assert np.array_equal(got.cpu().numpy(), want)
-    assert len(np.unique(want)) > 8  # not everything clamped
+    assert len(np.unique(want)) > (4 if pool else 8)  # not everything clamped (pooling pushes values to the top)
