@@ -51,6 +51,7 @@ STAGE_WORK = {
     "fc2_dequant": ("hbm", 512 + 40),
     # fused variants (pool folded into the producing conv): same ops, fewer bytes
     "conv2_pool": ("tensor", 75_497_472),
+    "conv1_conv2_pool": ("tensor", 3_538_944 + 75_497_472),  # conv1 + conv2 in one kernel (conv12_fused.cu)
     "conv4_pool": ("tensor", 75_497_472),
     "conv6_pool": ("tensor", 75_497_472),
 }

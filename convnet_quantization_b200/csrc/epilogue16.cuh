@@ -215,6 +215,105 @@ __device__ __forceinline__ void epi_block(uint32_t t_addr, EpiRegs<NCH>& K, cons
   }
 }
 
+// ------------------------------------------------------------------- low-register variants (conv12_fused.cu)
+// Same arithmetic as epi_block<SPLIT> / epi_block_pool for 16 channels per thread, shaped for a 128-register budget
+// and for a caller-supplied store: `store(half, s, packed)` receives the 16 bytes of pixel (half, s) of the thread.
+template <bool CHECK, class Consts, class Store, class Release>
+__device__ __forceinline__ void epi_block_store16(uint32_t t_addr, EpiRegs<16>& K, const Consts& consts, int ch0, bool fast,
+                                                  int zp_out, int lo, Store store, Release release) {
+  const int zp_sub = zp_out - (int)MAGIC_BITS;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t a = t_addr + ((uint32_t)(16 * half) << 16);
+    uint32_t v[32];
+    tmem_ld_frag<8>(a, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 64; c += 16) tmem_st_fill_16x16(a + c, K.fill);
+    if (half == 1) {
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      release();
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      uint32_t packed[4];
+      uint32_t bad = 0;
+      const uint32_t* w = v + 2 * s;
+      if (fast) {
+        packed[0] = epi_requant4<CHECK, 0>(w[0], w[1], w[4], w[5], K, zp_sub, lo, bad);
+        packed[1] = epi_requant4<CHECK, 4>(w[8], w[9], w[12], w[13], K, zp_sub, lo, bad);
+        packed[2] = epi_requant4<CHECK, 8>(w[16], w[17], w[20], w[21], K, zp_sub, lo, bad);
+        packed[3] = epi_requant4<CHECK, 12>(w[24], w[25], w[28], w[29], K, zp_sub, lo, bad);
+      }
+      if (!fast || (CHECK && __any_sync(0xffffffffu, requant_magic_out_of_range(bad)))) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          packed[g] = epi_requant4_exact(w[8 * g], w[8 * g + 1], w[8 * g + 4], w[8 * g + 5], consts, ch0 + 4 * g, zp_out, lo);
+      }
+      store(half, s, packed);
+    }
+  }
+}
+
+// 2x2 max-pool, one 16-column unit (4 channels of the thread) at a time, software-pipelined: the TMEM loads of unit
+// u+1 are in flight while unit u is pooled and requantised (32 accumulator registers live instead of 64).  The block is
+// re-armed and handed back once the last unit has been read.
+template <bool CHECK, class Consts, class Release>
+__device__ __forceinline__ void epi_block_pool16_units(uint32_t t_addr, EpiRegs<16>& K, const Consts& consts, int ch0,
+                                                       bool fast, int zp_out, int lo, uint8_t* out, bool valid, int lane,
+                                                       Release release) {
+  const int zp_sub = zp_out - (int)MAGIC_BITS;
+  const bool odd = (lane & 4) != 0;
+  constexpr uint32_t HALF1 = 16u << 16;
+  uint32_t packed[4];
+  uint32_t top[2][8], bot[2][8];
+  tmem_ld_frag<2>(t_addr, top[0]);          // block rows 0,1
+  tmem_ld_frag<2>(t_addr + HALF1, bot[0]);  // block rows 2,3
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    tmem_ld_wait();  // unit u has landed
+    if (u < 3) {
+      tmem_ld_frag<2>(t_addr + 16 * (u + 1), top[(u + 1) & 1]);
+      tmem_ld_frag<2>(t_addr + HALF1 + 16 * (u + 1), bot[(u + 1) & 1]);
+    }
+    const uint32_t(&tp)[8] = top[u & 1];
+    const uint32_t(&bt)[8] = bot[u & 1];
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // k = 2b + e  <-  registers 4b + 2s + e
+      const int i0 = 4 * (k >> 1) + (k & 1);
+      const uint32_t m0 = max(tp[i0], tp[i0 + 2]);
+      const uint32_t m1 = max(bt[i0], bt[i0 + 2]);
+      const uint32_t send = odd ? m0 : m1;
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 4);
+      r[k] = max(odd ? m1 : m0, recv);
+    }
+    if (u == 3) {  // everything read (no load in flight): re-arm the block and hand the slot back
+#pragma unroll
+      for (int c = 0; c < 64; c += 16) {
+        tmem_st_fill_16x16(t_addr + c, K.fill);
+        tmem_st_fill_16x16(t_addr + HALF1 + c, K.fill);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      release();
+    }
+    uint32_t bad = 0;
+    if (fast) {
+      if (u == 0) packed[0] = epi_requant4<CHECK, 0>(r[0], r[1], r[2], r[3], K, zp_sub, lo, bad);
+      if (u == 1) packed[1] = epi_requant4<CHECK, 4>(r[0], r[1], r[2], r[3], K, zp_sub, lo, bad);
+      if (u == 2) packed[2] = epi_requant4<CHECK, 8>(r[0], r[1], r[2], r[3], K, zp_sub, lo, bad);
+      if (u == 3) packed[3] = epi_requant4<CHECK, 12>(r[0], r[1], r[2], r[3], K, zp_sub, lo, bad);
+    }
+    if (!fast || (CHECK && __any_sync(0xffffffffu, requant_magic_out_of_range(bad))))
+      packed[u] = epi_requant4_exact(r[0], r[1], r[2], r[3], consts, ch0 + 4 * u, zp_out, lo);
+  }
+  if (valid) *reinterpret_cast<uint4*>(out) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
 // ------------------------------------------------------------------------------ no pooling, software-pipelined
 // The un-pooled layers (conv3, conv5; conv1) requantise every accumulator and are bound by their epilogue warps, which
 // with one block at a time idle through a TMEM round trip per block (both warps of a scheduler wait, read, compute and

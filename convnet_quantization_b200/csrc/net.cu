@@ -21,10 +21,29 @@ extern "C" int64_t b200q_static_workspace_bytes(int64_t b) {
 }
 
 namespace {
-// One entry per kernel the fused forward enqueues; order == launch order.
-const char* const kStageNames[] = {"quant_conv1", "conv2_pool", "conv3", "conv4_pool",
-                                   "conv5",       "conv6_pool", "fc1",   "fc2_dequant"};
-constexpr int kNumStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
+// One entry per kernel the fused forward enqueues; order == launch order.  B200Q_FUSE12=1 runs conv1 and conv2 as ONE
+// kernel (conv12_fused.cu: bit-exact, but measured slower than the two kernels - 1.05 ms against 0.39 + 0.48 ms at batch
+// 16 384 - because all its requantisation work lands on eight 128-register epilogue warps).
+const char* const kStageNamesFused[] = {"conv1_conv2_pool", "conv3", "conv4_pool", "conv5",
+                                        "conv6_pool",       "fc1",   "fc2_dequant"};
+const char* const kStageNamesSplit[] = {"quant_conv1", "conv2_pool", "conv3", "conv4_pool",
+                                        "conv5",       "conv6_pool", "fc1",   "fc2_dequant"};
+constexpr int kMaxStages = 8;
+
+bool fuse12_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200Q_FUSE12");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+bool fuse12_ok(const b200q_static_net* net) {
+  const b200q_conv3x3 &a = net->conv[0], &b = net->conv[1];
+  return fuse12_enabled() && a.corr_host && b.corr_host && a.rq.mult_host && a.rq.bdiv_host && b.rq.mult_host &&
+         b.rq.bdiv_host && (a.rq.flags & B200Q_RQ_BOUNDED) && a.cin == 4 && a.cout == 64 && a.img == 32 && b.cin == 64 &&
+         b.cout == 64 && b.img == 32 && b.zp_x == a.rq.zp_out;
+}
 
 // taps == nullptr: production path, 2x2 max-pools fused into the conv2/conv4/conv6 epilogues (8 kernels).
 // taps != nullptr: parity path, every reference op materialised (unfused convs + stand-alone pools) and copied out.
@@ -45,9 +64,13 @@ int forward_impl(const b200q_static_net* net, const float* x, float* logits, int
 
   if (taps == nullptr) {
     MARK();
-    STEP(b200q_quantize_conv3x3_first(x, A, b, net->in_inv_scale, &net->conv[0], stream));
-    MARK();
-    STEP(b200q_conv3x3_tc(A, B, b, &net->conv[1], 1, stream));  // -> [b,16,16,64]
+    if (fuse12_ok(net)) {
+      STEP(b200q_conv12_fused(x, B, b, net->in_inv_scale, &net->conv[0], &net->conv[1], stream));  // -> [b,16,16,64]
+    } else {
+      STEP(b200q_quantize_conv3x3_first(x, A, b, net->in_inv_scale, &net->conv[0], stream));
+      MARK();
+      STEP(b200q_conv3x3_tc(A, B, b, &net->conv[1], 1, stream));  // -> [b,16,16,64]
+    }
     MARK();
     STEP(b200q_conv3x3_tc(B, A, b, &net->conv[2], 0, stream));  // -> [b,16,16,128]
     MARK();
@@ -98,19 +121,27 @@ extern "C" int b200q_static_forward(const b200q_static_net* net, const float* x,
   return forward_impl(net, x, logits, b, workspace, workspace_bytes, taps, nullptr, stream);
 }
 
-extern "C" int b200q_static_num_stages(void) { return kNumStages; }
-extern "C" const char* b200q_static_stage_name(int i) { return (i >= 0 && i < kNumStages) ? kStageNames[i] : ""; }
+// Stage list of the production forward (seven stages with B200Q_FUSE12=1, else eight).
+extern "C" int b200q_static_num_stages(void) { return fuse12_enabled() ? 7 : 8; }
+extern "C" const char* b200q_static_stage_name(int i) {
+  const int n = b200q_static_num_stages();
+  if (i < 0 || i >= n) return "";
+  return fuse12_enabled() ? kStageNamesFused[i] : kStageNamesSplit[i];
+}
 
 extern "C" int b200q_static_forward_profiled(const b200q_static_net* net, const float* x, float* logits, int64_t b,
                                              void* workspace, int64_t workspace_bytes, float* stage_ms_host,
                                              void* stream) {
   B200Q_REQUIRE(stage_ms_host != nullptr, "static_forward_profiled: null stage_ms_host");
-  static thread_local cudaEvent_t ev[kNumStages + 1];
+  const int kNumStages = b200q_static_num_stages();
+  B200Q_REQUIRE(!fuse12_enabled() || fuse12_ok(net),
+                "static_forward_profiled: net does not qualify for the fused conv1+conv2 stage; unset B200Q_FUSE12");
+  static thread_local cudaEvent_t ev[kMaxStages + 1];
   static thread_local int ev_device = -1;
   int dev = -1;
   B200Q_CUDA(cudaGetDevice(&dev));
   if (ev_device != dev) {  // events belong to a device: (re)create on first use per thread/device
-    for (int i = 0; i <= kNumStages; ++i) B200Q_CUDA(cudaEventCreate(&ev[i]));
+    for (int i = 0; i <= kMaxStages; ++i) B200Q_CUDA(cudaEventCreate(&ev[i]));
     ev_device = dev;
   }
   for (int i = 0; i < kNumStages; ++i) stage_ms_host[i] = 0.f;

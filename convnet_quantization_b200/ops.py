@@ -120,6 +120,17 @@ def quantize_conv2d_first(x: torch.Tensor, scale: float, w: PackedConv) -> torch
     return y
 
 
+def quantize_conv2d_conv2d_pool(x: torch.Tensor, scale: float, w1: PackedConv, w2: PackedConv) -> torch.Tensor:
+    """fp32 NCHW ``[B,3,32,32]`` -> quantize -> conv1+ReLU -> conv2+ReLU -> 2x2 max-pool -> uint8 NHWC ``[B,16,16,64]``
+    in one kernel (``b200q_conv12_fused``)."""
+    _need_cuda(x)
+    b = x.shape[0]
+    y = torch.empty((b, w2.img // 2, w2.img // 2, w2.cout), dtype=_U8, device=x.device)
+    _lib.check(_lib.load().b200q_conv12_fused(x.data_ptr(), y.data_ptr(), b, _inv_scale(scale), w1.ptr(), w2.ptr(),
+                                              _stream()), "conv12_fused")
+    return y
+
+
 def linear_q(x: torch.Tensor, w: PackedLinear, impl: str = "tc") -> torch.Tensor:
     _need_cuda(x)
     b = x.shape[0]

@@ -109,6 +109,13 @@ int b200q_conv3x3_first(const uint8_t* x, uint8_t* y, int64_t b, const b200q_con
 /* Fused aten::quantize_per_tensor + first conv: fp32 NCHW [b,3,img,img] -> uint8 NHWC [b,img,img,cout]. */
 int b200q_quantize_conv3x3_first(const float* x, uint8_t* y, int64_t b, float inv_scale,
                                  const b200q_conv3x3* L, void* stream);
+/* The first two layers and the first max-pool in one kernel (conv1's output never leaves shared memory):
+ * aten::quantize_per_tensor + quantized::conv2d + relu (L1: cin 4, cout 64, img 32) + quantized::conv2d + relu
+ * (L2: cin 64, cout 64) + aten::quantized_max_pool2d: fp32 NCHW [b,3,32,32] -> uint8 NHWC [b,16,16,64].
+ * Reference call sites: models/baseline_model.py:60-66 on the converted net.  Both layers need host mirrors of
+ * their constants and L1 must be B200Q_RQ_BOUNDED; otherwise B200Q_ERR_INVALID_ARG (use the separate entry points). */
+int b200q_conv12_fused(const float* x, uint8_t* y, int64_t b, float inv_scale, const b200q_conv3x3* L1,
+                       const b200q_conv3x3* L2, void* stream);
 /* tcgen05 implicit-GEMM 3x3 conv (cin % 64 == 0): uint8 NHWC [b,img,img,cin] -> uint8 NHWC [b,img,img,cout]
  * or, with pool2x2 != 0, the 2x2/2 max-pooled [b,img/2,img/2,cout] (aten::quantized_max_pool2d fused). */
 int b200q_conv3x3_tc(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, int pool2x2, void* stream);

@@ -192,3 +192,25 @@ def test_conv_tc_requant_fallback_paths(qparams, name, mode, pool):
     torch.cuda.synchronize()
     assert np.array_equal(got.cpu().numpy(), want)
     assert len(np.unique(want)) > (4 if pool else 8)  # not everything clamped (pooling pushes values to the top)
+
+
+@pytest.mark.parametrize("b,gain", [(1, 1.0), (3, 1.0), (149, 1.0), (300, 1.0), (5, 4.0)])
+def test_conv12_fused(qparams, qparams_np, b, gain):
+    """quantize + conv1 + conv2 + 2x2 max-pool in one kernel (conv1's output never leaves shared memory) == the oracle's
+    four ops, including CTAs that process several images and inputs far outside the calibrated range."""
+    from convnet_quantization_b200 import ops, synth
+    from oracle import int_ops as IO
+    pc1, s, zp = _packed(qparams, "conv1")
+    pc2, s1, zp1 = _packed(qparams, "conv2")
+    x = synth.images_f32(b, seed=100 + b) * gain
+    xq = IO.quantize_per_tensor(x.numpy().transpose(0, 2, 3, 1), s, zp)
+    c1 = _want_conv(xq, s, zp, qparams_np["conv1"])
+    want = IO.max_pool2x2(_want_conv(c1, s1, zp1, qparams_np["conv2"]))
+    got = ops.quantize_conv2d_conv2d_pool(x.cuda(), s, pc1, pc2)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    bad = got != want
+    assert not bad.any(), f"b={b}: {int(bad.sum())} / {bad.size} mismatches; first at {np.argwhere(bad)[:5].tolist()}"
+    # and the two-kernel path it replaces
+    two = ops.conv2d_q(ops.quantize_conv2d_first(x.cuda(), s, pc1), pc2, pool2x2=True).cpu().numpy()
+    assert np.array_equal(two, want)
