@@ -298,6 +298,26 @@ def run_ours(args):
            "api": "StaticPTQModel().quantize() -> model(x_cpu_pinned) -> cpu logits"}
     assert torch.equal(out_host, logits.cpu()), "e2e logits differ from the device-resident run"
 
+    # ---- the same call on the uint8 data path (extra key, NOT the contract's e2e): raw uint8 NHWC
+    #      pixels from pinned host memory -> host logits; a quarter of the bytes cross PCIe.  Its inputs are other images
+    #      (the fp32 batch above was normalised on the device), so only determinism is checked here; bit-identity with
+    #      the fp32 route is a parity test (tests/test_gpu_net.py).
+    pix_host = torch.randint(0, 256, (B, 32, 32, 3), dtype=torch.uint8,
+                             generator=torch.Generator().manual_seed(1000 + rank)).pin_memory()
+    for _ in range(2):
+        out_u8 = qmodel.forward_uint8(pix_host)
+    barrier()
+    ev0.record()
+    for _ in range(e2e_steps):
+        out_u8_2 = qmodel.forward_uint8(pix_host)
+    ev1.record()
+    barrier()
+    u8_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    assert torch.equal(out_u8, out_u8_2)
+    e2e_u8 = {"value": world * B * e2e_steps / (u8_ms * 1e-3), "unit": UNIT, "steps": e2e_steps,
+              "h2d_bytes_per_step": pix_host.numel(), "d2h_bytes_per_step": out_u8.numel() * out_u8.element_size(),
+              "api": "model.forward_uint8(pixels_cpu_pinned uint8 NHWC) -> cpu logits"}
+
     # ---- correct-count: the only collective, off the hot path (one NCCL all-reduce of 3 int64)
     from convnet_quantization_b200 import sharding
     counts = [int(v) for v in sharding.allreduce_counts(sharding.topk_counts(logits, labels)).tolist()]
@@ -321,7 +341,7 @@ def run_ours(args):
             "config": {"workload": "static-PTQ int8 SimpleConvNet forward, CIFAR-10 shape fp32 [B,3,32,32] -> logits [B,10]",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-sharded x{world}",
                        "l2": f"input {x.numel() * 4 / 2**20:.0f} MiB + activations > 126 MiB L2 (no flush needed)"},
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "clocks": clocks.summary(), "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "eval": {"top1": counts[0], "top5": counts[1], "total": counts[2]},
         }
         print(json.dumps(line), flush=True)

@@ -26,9 +26,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 EXPORTS = (
     "b200q_last_error", "b200q_abi_version", "b200q_launch_count", "b200q_quantize_nchw_to_nhwc", "b200q_quantize_flat",
     "b200q_dequantize", "b200q_relu_q", "b200q_max_pool2x2_nhwc", "b200q_minmax", "b200q_conv3x3_first",
-    "b200q_quantize_conv3x3_first", "b200q_conv12_fused", "b200q_conv3x3_tc", "b200q_conv3x3_simt", "b200q_linear_tc",
+    "b200q_quantize_conv3x3_first", "b200q_u8_conv3x3_first", "b200q_conv12_fused", "b200q_conv3x3_tc", "b200q_conv3x3_simt", "b200q_linear_tc",
     "b200q_linear_simt", "b200q_linear_dequant", "b200q_linear_dynamic", "b200q_static_workspace_bytes",
-    "b200q_static_forward", "b200q_static_num_stages", "b200q_static_stage_name", "b200q_static_forward_profiled",
+    "b200q_static_forward", "b200q_static_forward_u8", "b200q_static_num_stages", "b200q_static_stage_name", "b200q_static_forward_profiled",
 )
 
 
@@ -115,6 +115,8 @@ _SIGNATURES = {
     "b200q_minmax": [_P, _L, _P, _P, _P],
     "b200q_conv3x3_first": [_P, _P, _L, C.POINTER(Conv3x3), _P],
     "b200q_quantize_conv3x3_first": [_P, _P, _L, _F, C.POINTER(Conv3x3), _P],
+    "b200q_u8_conv3x3_first": [_P, _P, _L, _P, C.POINTER(Conv3x3), _P],
+    "b200q_static_forward_u8": [C.POINTER(StaticNet), _P, _P, _P, _L, _P, _L, _P],
     "b200q_conv12_fused": [_P, _P, _L, _F, C.POINTER(Conv3x3), C.POINTER(Conv3x3), _P],
     "b200q_conv3x3_tc": [_P, _P, _L, C.POINTER(Conv3x3), _I, _P],
     "b200q_conv3x3_simt": [_P, _P, _L, C.POINTER(Conv3x3), _P],

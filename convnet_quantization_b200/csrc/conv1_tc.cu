@@ -36,10 +36,19 @@ constexpr int C1_A_TILE = 128 * C1_KB, C1_A_BYTES = C1_TILES * C1_A_TILE;  // 4 
 constexpr int C1_B_BYTES = C1_COUT * C1_KB;
 constexpr int C1_QP = C1_IMG + 2;                            // padded quantised image pitch (words)
 constexpr int C1_Q_BYTES = (C1_QP * C1_QP * 4 + 15) / 16 * 16;
-constexpr int C1_SMEM = 2 * C1_A_BYTES + C1_B_BYTES + C1_Q_BYTES + 256 + 1024;
+constexpr int C1_LUT_BYTES = 3 * 256;
+constexpr int C1_SMEM = 2 * C1_A_BYTES + C1_B_BYTES + C1_Q_BYTES + 256 + C1_LUT_BYTES + 1024;
+
+// uint8 input path: raw uint8 NHWC pixels [b,32,32,3] go through a per-channel 256-entry table
+// lut[c][v] = quantize_per_tensor(Normalize(ToTensor(v))) that the host builds with the reference's own torch CPU ops,
+// so the result is bit-identical to quantising the fp32 tensor the reference's DataLoader would have produced.
+struct C1Lut {
+  uint8_t q[3][256];
+};
 
 struct C1Args {
   const float* x;
+  const uint8_t* xu8;  // uint8 NHWC [b,32,32,3] (U8IN kernels), else null
   uint8_t* y;
   const int8_t* w;     // [64][9][4] (cin padded to 4), device
   int64_t n_img;
@@ -63,9 +72,9 @@ __device__ __forceinline__ uint32_t quantize_magic(float x, float inv_scale, int
   return (uint32_t)max(0, min(q, 255));
 }
 
-template <bool CHECK>
+template <bool CHECK, bool U8IN>
 __global__ void __launch_bounds__(C1_THREADS, 1)
-conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
+conv1_tc_kernel(const __grid_constant__ C1Consts consts, const __grid_constant__ C1Lut lut, const C1Args args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_smem = smem;                                   // [2][8 tiles][128 rows][32 B]
@@ -76,6 +85,7 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
   uint64_t* tmem_empty_bar = tmem_full_bar + C1_SLOTS;      // [C1_SLOTS]
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + C1_SLOTS);
   uint32_t* magic_smem = tmem_base_smem + 1;  // holds MAGIC_BITS (epilogue16.cuh epi_init)
+  uint8_t* lut_smem = reinterpret_cast<uint8_t*>(empty_bar) + 256;  // [3][256] (U8IN)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,6 +106,10 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
   }
   if (warp < C1_EPI_WARPS) {
     const int t = threadIdx.x;
+    if constexpr (U8IN) {
+      for (int i = t; i < C1_LUT_BYTES / 4; i += 32 * C1_EPI_WARPS)
+        reinterpret_cast<uint32_t*>(lut_smem)[i] = reinterpret_cast<const uint32_t*>(&lut.q[0][0])[i];
+    }
     // border of the quantised image = zero-point, once
     for (int i = t; i < C1_QP * C1_QP; i += 32 * C1_EPI_WARPS) {
       const int r = i / C1_QP, c = i % C1_QP;
@@ -144,21 +158,42 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
     // thread p owns image row p/4, columns 8*(p%4) .. +7 of the fp32 planes.  The loads of image it+1 are issued right
     // after image it has been quantised, so their HBM latency overlaps the im2col pass and the barrier waits.
     const int row = p >> 2, col0 = (p & 3) * 8;
-    float4 v[3][2];
+    float4 v[3][2];   // fp32 input: three planes x 8 pixels
+    uint2 u[3];       // uint8 NHWC input: 8 pixels x 3 bytes = 24 contiguous bytes
     auto load_image = [&](int it) {
       const int64_t img = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
-      const float* src = args.x + img * (3 * C1_IMG * C1_IMG) + row * C1_IMG + col0;
+      if constexpr (U8IN) {
+        const uint8_t* src = args.xu8 + img * (3 * C1_IMG * C1_IMG) + (row * C1_IMG + col0) * 3;
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        v[ch][0] = __ldg(reinterpret_cast<const float4*>(src + ch * C1_IMG * C1_IMG));
-        v[ch][1] = __ldg(reinterpret_cast<const float4*>(src + ch * C1_IMG * C1_IMG) + 1);
+        for (int i = 0; i < 3; ++i) u[i] = __ldg(reinterpret_cast<const uint2*>(src) + i);
+      } else {
+        const float* src = args.x + img * (3 * C1_IMG * C1_IMG) + row * C1_IMG + col0;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          v[ch][0] = __ldg(reinterpret_cast<const float4*>(src + ch * C1_IMG * C1_IMG));
+          v[ch][1] = __ldg(reinterpret_cast<const float4*>(src + ch * C1_IMG * C1_IMG) + 1);
+        }
       }
     };
     if (my_imgs > 0) load_image(0);
     for (int it = 0; it < my_imgs; ++it) {
       const int buf = it & 1;
       // ---- (1) quantise
-      {
+      if constexpr (U8IN) {
+        uint32_t* dst = q_img + (row + 1) * C1_QP + col0 + 1;
+        const uint32_t wds[6] = {u[0].x, u[0].y, u[1].x, u[1].y, u[2].x, u[2].y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // pixel j = bytes 3j, 3j+1, 3j+2 of the 24
+          uint32_t word = zp_hi;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            const int byte = 3 * j + ch;
+            const uint32_t pix = (wds[byte >> 2] >> (8 * (byte & 3))) & 0xffu;
+            word |= (uint32_t)lut_smem[ch * 256 + pix] << (8 * ch);
+          }
+          dst[j] = word;
+        }
+      } else {
         uint32_t* dst = q_img + (row + 1) * C1_QP + col0 + 1;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -252,9 +287,9 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const C1Args args) {
   }
 }
 
-// Returns 1 when the layer cannot take this path (no host mirrors / constants not flagged as bounded).
-int conv1_tc_dispatch(const float* x, uint8_t* y, int64_t b, float inv_scale, const b200q_conv3x3* L, cudaStream_t s,
-                      int* rc) {
+// x: fp32 NCHW input (lut_host == nullptr) or, with lut_host = uint8[3][256] on the HOST, xu8: uint8 NHWC input.
+static int conv1_tc_launch(const float* x, const uint8_t* xu8, const uint8_t* lut_host, uint8_t* y, int64_t b, float inv_scale,
+                           const b200q_conv3x3* L, cudaStream_t s, int* rc) {
   const b200q_requant& rq = L->rq;
   if (!L->corr_host || !rq.mult_host || !rq.bdiv_host || !(rq.flags & B200Q_RQ_BOUNDED)) return 1;
   if (L->cin != 4 || L->cout != C1_COUT || L->img != C1_IMG) return 1;
@@ -266,20 +301,51 @@ int conv1_tc_dispatch(const float* x, uint8_t* y, int64_t b, float inv_scale, co
     consts.bdiv[c] = rq.bdiv_host[c];
     consts.mult[c] = rq.mult_host[c];
   }
+  C1Lut lut;
+  const bool u8in = lut_host != nullptr;
+  if (u8in)
+    for (int i = 0; i < 3 * 256; ++i) lut.q[i / 256][i % 256] = lut_host[i];
+  else
+    for (int i = 0; i < 3 * 256; ++i) lut.q[i / 256][i % 256] = 0;
   const bool check = !(rq.flags & B200Q_RQ_ACC22);
-  auto kernel = check ? conv1_tc_kernel<true> : conv1_tc_kernel<false>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[check]) {
+  void (*kernel)(C1Consts, C1Lut, C1Args) =
+      u8in ? (check ? conv1_tc_kernel<true, true> : conv1_tc_kernel<false, true>)
+           : (check ? conv1_tc_kernel<true, false> : conv1_tc_kernel<false, false>);
+  static bool attr_set[4] = {false, false, false, false};
+  const int idx = (u8in ? 2 : 0) + (check ? 1 : 0);
+  if (!attr_set[idx]) {
     *rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM),
                      "cudaFuncSetAttribute(conv1_tc_kernel)");
     if (*rc) return 0;
-    attr_set[check] = true;
+    attr_set[idx] = true;
   }
-  C1Args args{x, y, L->w, b, inv_scale, L->zp_x, rq.zp_out, rq.relu ? rq.zp_out : 0, 1};
+  C1Args args{x, xu8, y, L->w, b, inv_scale, L->zp_x, rq.zp_out, rq.relu ? rq.zp_out : 0, 1};
   const int grid = b < num_sms() ? (int)b : num_sms();
-  kernel<<<grid, C1_THREADS, C1_SMEM, s>>>(consts, args);
+  kernel<<<grid, C1_THREADS, C1_SMEM, s>>>(consts, lut, args);
   *rc = launched("conv1_tc_kernel");
   return 0;
 }
 
+// Returns 1 when the layer cannot take this path (no host mirrors / constants not flagged as bounded).
+int conv1_tc_dispatch(const float* x, uint8_t* y, int64_t b, float inv_scale, const b200q_conv3x3* L, cudaStream_t s,
+                      int* rc) {
+  return conv1_tc_launch(x, nullptr, nullptr, y, b, inv_scale, L, s, rc);
+}
+
 }  // namespace b200q
+
+using namespace b200q;
+
+extern "C" int b200q_u8_conv3x3_first(const uint8_t* x_nhwc, uint8_t* y, int64_t b, const uint8_t* lut_host,
+                                      const b200q_conv3x3* L, void* stream) {
+  B200Q_REQUIRE(L && lut_host && ((x_nhwc && y) || b == 0), "u8_conv3x3_first: null pointer");
+  B200Q_REQUIRE((uintptr_t)x_nhwc % 8 == 0 && (uintptr_t)y % 16 == 0, "u8_conv3x3_first: misaligned buffers");
+  if (b == 0) return 0;
+  int rc = 0;
+  if (conv1_tc_launch(nullptr, x_nhwc, lut_host, y, b, 0.f, L, (cudaStream_t)stream, &rc) != 0) {
+    set_error("u8_conv3x3_first: layer must be conv1 (cin 4, cout 64, img 32) with host mirrors and B200Q_RQ_BOUNDED");
+    return B200Q_ERR_INVALID_ARG;
+  }
+  return rc;
+}
+

@@ -48,8 +48,9 @@ bool fuse12_ok(const b200q_static_net* net) {
 // taps == nullptr: production path, 2x2 max-pools fused into the conv2/conv4/conv6 epilogues (8 kernels).
 // taps != nullptr: parity path, every reference op materialised (unfused convs + stand-alone pools) and copied out.
 int forward_impl(const b200q_static_net* net, const float* x, float* logits, int64_t b, void* workspace,
-                 int64_t workspace_bytes, uint8_t* const* taps, cudaEvent_t* ev, void* stream) {
-  B200Q_REQUIRE(net && ((x && logits && workspace) || b == 0), "static_forward: null pointer");
+                 int64_t workspace_bytes, uint8_t* const* taps, cudaEvent_t* ev, void* stream,
+                 const uint8_t* x_u8 = nullptr, const uint8_t* lut_host = nullptr) {
+  B200Q_REQUIRE(net && (((x || x_u8) && logits && workspace) || b == 0), "static_forward: null pointer");
   B200Q_REQUIRE(b >= 0, "static_forward: negative batch");
   if (b == 0) return 0;
   B200Q_REQUIRE(workspace_bytes >= b200q_static_workspace_bytes(b), "static_forward: workspace too small (%lld < %lld)",
@@ -64,7 +65,11 @@ int forward_impl(const b200q_static_net* net, const float* x, float* logits, int
 
   if (taps == nullptr) {
     MARK();
-    if (fuse12_ok(net)) {
+    if (x_u8) {  // uint8 data path: table look-up instead of the fp32 quantiser, same kernel otherwise
+      STEP(b200q_u8_conv3x3_first(x_u8, A, b, lut_host, &net->conv[0], stream));
+      MARK();
+      STEP(b200q_conv3x3_tc(A, B, b, &net->conv[1], 1, stream));
+    } else if (fuse12_ok(net)) {
       STEP(b200q_conv12_fused(x, B, b, net->in_inv_scale, &net->conv[0], &net->conv[1], stream));  // -> [b,16,16,64]
     } else {
       STEP(b200q_quantize_conv3x3_first(x, A, b, net->in_inv_scale, &net->conv[0], stream));
@@ -122,6 +127,13 @@ extern "C" int b200q_static_forward(const b200q_static_net* net, const float* x,
 }
 
 // Stage list of the production forward (seven stages with B200Q_FUSE12=1, else eight).
+extern "C" int b200q_static_forward_u8(const b200q_static_net* net, const uint8_t* x_nhwc, const uint8_t* lut_host,
+                                       float* logits, int64_t b, void* workspace, int64_t workspace_bytes,
+                                       void* stream) {
+  B200Q_REQUIRE(lut_host != nullptr && (x_nhwc != nullptr || b == 0), "static_forward_u8: null pointer");
+  return forward_impl(net, nullptr, logits, b, workspace, workspace_bytes, nullptr, nullptr, stream, x_nhwc, lut_host);
+}
+
 extern "C" int b200q_static_num_stages(void) { return fuse12_enabled() ? 7 : 8; }
 extern "C" const char* b200q_static_stage_name(int i) {
   const int n = b200q_static_num_stages();

@@ -70,6 +70,27 @@ class StaticEngine:
 
     __call__ = forward
 
+    @torch.no_grad()
+    def forward_u8(self, x_u8: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """uint8 data path: raw pixels, uint8 NHWC ``[B,32,32,3]`` (CUDA) -> fp32 logits ``[B,10]``; bit-identical to
+        ``forward(synth.normalize(pixels))`` (``packing.input_lut``)."""
+        if not x_u8.is_cuda or x_u8.dtype != torch.uint8:
+            raise _lib.B200QError("StaticEngine.forward_u8 expects a CUDA uint8 tensor")
+        x_u8 = x_u8.contiguous()
+        if x_u8.dim() != 4 or tuple(x_u8.shape[1:]) != (32, 32, 3):
+            raise _lib.B200QError(f"expected uint8 NHWC [B,32,32,3] input, got {tuple(x_u8.shape)}")
+        b = x_u8.shape[0]
+        with torch.cuda.device(self.device):
+            logits = out if out is not None else torch.empty((b, 10), dtype=torch.float32, device=self.device)
+            if b == 0:
+                return logits
+            ws = self._workspace(b)
+            rc = self.lib.b200q_static_forward_u8(self.packed.ptr(), x_u8.data_ptr(), self.packed.input_lut.data_ptr(),
+                                                  logits.data_ptr(), b, ws.data_ptr(), ws.numel(),
+                                                  torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc, "static_forward_u8")
+        return logits
+
     def stage_names(self):
         return [self.lib.b200q_static_stage_name(i).decode() for i in range(self.lib.b200q_static_num_stages())]
 

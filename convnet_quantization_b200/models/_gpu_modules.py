@@ -97,20 +97,22 @@ class B200StaticQuantizedNet(_GpuResident):
             self._pipe = {
                 "streams": [torch.cuda.Stream(dev), torch.cuda.Stream(dev)],
                 "x": [torch.empty((self.HOST_CHUNK, 3, 32, 32), dtype=torch.float32, device=dev) for _ in range(2)],
+                "xu8": None,  # uint8 NHWC staging buffers, allocated on first use of forward_uint8
                 "y": [torch.empty((self.HOST_CHUNK, 10), dtype=torch.float32, device=dev) for _ in range(2)],
                 "out": None,
             }
         return self._pipe
 
-    def _chunks(self, b: int):
+    def _chunks(self, b: int, chunk: int | None = None):
         """(offset, size) of the pipelined chunks.  The copies run back to back, so the un-overlapped part of a call is
         the kernels of the LAST chunk; the final ``HOST_CHUNK`` images are therefore split 3/4 + 1/4 (one extra chunk:
         every chunk costs ~30 us of fixed overhead, and chunks much smaller than 512 images take longer to compute than
         to copy - measured, scripts/gpu_e2e_chunks.sh)."""
+        chunk = chunk or self.HOST_CHUNK
         lo = 0
-        while b - lo > self.HOST_CHUNK:
-            yield lo, self.HOST_CHUNK
-            lo += self.HOST_CHUNK
+        while b - lo > chunk:
+            yield lo, chunk
+            lo += chunk
         rest = b - lo
         tail = rest // 4
         if tail >= self.TAIL_MIN:
@@ -118,22 +120,31 @@ class B200StaticQuantizedNet(_GpuResident):
             lo += rest - tail
         yield lo, b - lo
 
-    def _forward_host(self, x: torch.Tensor) -> torch.Tensor:
+    def _forward_host(self, x: torch.Tensor, u8: bool = False) -> torch.Tensor:
         b = x.shape[0]
         x = x.contiguous()
         pipe = self._pipeline()
+        # uint8 pixels are a quarter of the bytes: four times the images per chunk (same 24 MiB per copy), which also
+        # keeps the kernels at an efficient batch size on a path that is compute- rather than PCIe-bound
+        chunk = 4 * self.HOST_CHUNK if u8 else self.HOST_CHUNK
+        if u8 and pipe["xu8"] is None:
+            pipe["xu8"] = [torch.empty((chunk, 32, 32, 3), dtype=torch.uint8, device=self.engine_device) for _ in range(2)]
+            pipe["yu8"] = [torch.empty((chunk, 10), dtype=torch.float32, device=self.engine_device) for _ in range(2)]
         if pipe["out"] is None or pipe["out"].shape[0] < b:
             pipe["out"] = torch.empty((max(b, self.HOST_CHUNK), 10), dtype=torch.float32).pin_memory()
         out = pipe["out"][:b]
         cur = torch.cuda.current_stream(self.engine_device)
         for s in pipe["streams"]:
             s.wait_stream(cur)
-        for i, (lo, n) in enumerate(self._chunks(b)):
+        for i, (lo, n) in enumerate(self._chunks(b, chunk)):
             k = i & 1
             with torch.cuda.stream(pipe["streams"][k]):  # per-stream buffers: reuse is ordered by the stream itself
-                xin, yout = pipe["x"][k][:n], pipe["y"][k][:n]
+                xin, yout = (pipe["xu8"] if u8 else pipe["x"])[k][:n], (pipe["yu8"] if u8 else pipe["y"])[k][:n]
                 xin.copy_(x[lo:lo + n], non_blocking=True)
-                self.engine.forward(xin, out=yout)
+                if u8:
+                    self.engine.forward_u8(xin, out=yout)
+                else:
+                    self.engine.forward(xin, out=yout)
                 out[lo:lo + n].copy_(yout, non_blocking=True)
         for s in pipe["streams"]:
             s.synchronize()
@@ -144,6 +155,19 @@ class B200StaticQuantizedNet(_GpuResident):
         if not x.is_cuda and x.dim() == 4 and x.shape[0] > 0:
             return self._forward_host(x.float())
         return self._run(x, self.engine.forward)
+
+    @torch.no_grad()
+    def forward_uint8(self, pixels: torch.Tensor) -> torch.Tensor:
+        """uint8 data path: raw pixels, uint8 NHWC ``[B,32,32,3]`` as ``torchvision``'s CIFAR-10
+        ``.data`` holds them, CPU or CUDA -> fp32 logits on the input's device.  Bit-identical to
+        ``forward(Normalize(ToTensor(pixels)))``; a quarter of the bytes cross PCIe."""
+        if pixels.dtype != torch.uint8 or pixels.dim() != 4 or tuple(pixels.shape[1:]) != (32, 32, 3):
+            raise _lib.B200QError(f"forward_uint8 expects uint8 NHWC [B,32,32,3], got {pixels.dtype} {tuple(pixels.shape)}")
+        if not pixels.is_cuda and pixels.shape[0] > 0:
+            return self._forward_host(pixels, u8=True)
+        if not pixels.is_cuda:
+            return torch.empty((0, 10), dtype=torch.float32)
+        return self.engine.forward_u8(pixels)
 
     @torch.no_grad()
     def forward_with_taps(self, x):

@@ -72,6 +72,23 @@ def conv_border_corr(w_int8: torch.Tensor, zp_x: int) -> torch.Tensor:
     return torch.stack(rows).to(torch.int32).contiguous()
 
 
+def input_lut(in_scale: float, in_zp: int, mean=None, std=None) -> torch.Tensor:
+    """uint8 ``[3][256]`` table for the uint8 data path: ``lut[c][v]`` is what the reference pipeline makes of a raw
+    pixel value ``v`` in channel ``c`` — ``ToTensor`` (``v/255``), ``Normalize(mean, std)``
+    (``utils/dataset_manager.py:41-44``) and the model's ``QuantStub`` (``aten::quantize_per_tensor``) — computed here
+    with those very torch CPU ops, so the GPU look-up is bit-identical to quantising the fp32 tensor."""
+    from . import synth
+    v = torch.arange(256, dtype=torch.uint8).view(256, 1, 1, 1).expand(256, 3, 1, 1).contiguous()
+    if mean is None and std is None:
+        x = synth.normalize(v)
+    else:
+        m = torch.tensor(mean, dtype=torch.float32).view(1, 3, 1, 1)
+        sd = torch.tensor(std, dtype=torch.float32).view(1, 3, 1, 1)
+        x = ((v.to(torch.float32) / 255.0) - m) / sd
+    q = torch.quantize_per_tensor(x, float(in_scale), int(in_zp), torch.quint8).int_repr()
+    return q.view(256, 3).t().contiguous()  # [3][256]
+
+
 class PackedConv:
     def __init__(self, name, layer, s_x, zp_x, device, relu=True):
         cin, cout, img = CONV_GEOMETRY[name]
@@ -141,6 +158,7 @@ class PackedStaticNet:
         s, zp = float(qp["fc1"]["out_scale"]), int(qp["fc1"]["out_zp"])
         self.fc2 = PackedLinear("fc2", qp["fc2"], s, zp, self.device, relu=False)
         self.out_scale, self.out_zp = float(qp["fc2"]["out_scale"]), int(qp["fc2"]["out_zp"])
+        self.input_lut = input_lut(self.in_scale, self.in_zp)  # host uint8 [3][256] (uint8 data path)
         net = _lib.StaticNet()
         net.in_inv_scale, net.in_zp = self.in_inv_scale, self.in_zp
         for i, pc in enumerate(self.convs):

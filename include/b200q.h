@@ -109,6 +109,13 @@ int b200q_conv3x3_first(const uint8_t* x, uint8_t* y, int64_t b, const b200q_con
 /* Fused aten::quantize_per_tensor + first conv: fp32 NCHW [b,3,img,img] -> uint8 NHWC [b,img,img,cout]. */
 int b200q_quantize_conv3x3_first(const float* x, uint8_t* y, int64_t b, float inv_scale,
                                  const b200q_conv3x3* L, void* stream);
+/* uint8 data path (the step before the model in the reference: utils/dataset_manager.py:41-44 ToTensor + Normalize,
+ * then QuantStub): raw uint8 NHWC pixels [b,32,32,3] -> conv1 output uint8 NHWC [b,32,32,64].  lut_host is a HOST
+ * table uint8[3][256], lut[c][v] = quantize_per_tensor(Normalize(ToTensor(v)))[c], built by the caller with the
+ * reference's own torch ops (convnet_quantization_b200.packing.input_lut), so results are bit-identical to the fp32
+ * route.  L must be conv1 (cin 4, cout 64, img 32) with host mirrors and B200Q_RQ_BOUNDED. */
+int b200q_u8_conv3x3_first(const uint8_t* x_nhwc, uint8_t* y, int64_t b, const uint8_t* lut_host,
+                           const b200q_conv3x3* L, void* stream);
 /* The first two layers and the first max-pool in one kernel (conv1's output never leaves shared memory):
  * aten::quantize_per_tensor + quantized::conv2d + relu (L1: cin 4, cout 64, img 32) + quantized::conv2d + relu
  * (L2: cin 64, cout 64) + aten::quantized_max_pool2d: fp32 NCHW [b,3,32,32] -> uint8 NHWC [b,16,16,64].
@@ -161,6 +168,9 @@ int b200q_static_forward(const b200q_static_net* net, const float* x, float* log
  * durations in milliseconds to stage_ms_host (HOST memory).  Stage i is named b200q_static_stage_name(i). */
 int b200q_static_num_stages(void);
 const char* b200q_static_stage_name(int i);
+/* Same forward from raw uint8 NHWC pixels [b,32,32,3] (see b200q_u8_conv3x3_first for lut_host). */
+int b200q_static_forward_u8(const b200q_static_net* net, const uint8_t* x_nhwc, const uint8_t* lut_host, float* logits,
+                            int64_t b, void* workspace, int64_t workspace_bytes, void* stream);
 int b200q_static_forward_profiled(const b200q_static_net* net, const float* x, float* logits, int64_t b,
                                   void* workspace, int64_t workspace_bytes, float* stage_ms_host, void* stream);
 

@@ -79,3 +79,30 @@ def test_static_forward_large_batch_properties(engine, oracle_model):
 def test_empty_batch(engine):
     out = engine.forward(torch.empty(0, 3, 32, 32, device="cuda"))
     assert tuple(out.shape) == (0, 10)
+
+
+@pytest.mark.parametrize("b", [1, 5, 300])
+def test_uint8_data_path_is_bit_identical(engine, b):
+    """Raw uint8 NHWC pixels through the look-up-table quantiser == the fp32 route (ToTensor + Normalize on the CPU, then
+    QuantStub), logits bit for bit."""
+    from convnet_quantization_b200 import synth
+    g = torch.Generator().manual_seed(40 + b)
+    pix = torch.randint(0, 256, (b, 32, 32, 3), dtype=torch.uint8, generator=g)
+    pix[0, :4] = 0
+    pix[0, 4:8] = 255
+    want = engine.forward(synth.normalize(pix.permute(0, 3, 1, 2)).contiguous().cuda())
+    got = engine.forward_u8(pix.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+
+
+def test_uint8_data_path_host_pipeline(golden_qparams):
+    from convnet_quantization_b200 import synth
+    from convnet_quantization_b200.models._gpu_modules import B200StaticQuantizedNet
+    net = B200StaticQuantizedNet(golden_qparams, "cuda")
+    g = torch.Generator().manual_seed(9)
+    pix = torch.randint(0, 256, (5000, 32, 32, 3), dtype=torch.uint8, generator=g)
+    want = net(synth.normalize(pix.permute(0, 3, 1, 2)).contiguous())
+    got = net.forward_uint8(pix)
+    assert not got.is_cuda and torch.equal(got, want)
+    assert torch.equal(net.forward_uint8(pix.cuda()).cpu(), want)

@@ -77,3 +77,20 @@ def test_requant_constants_match_numpy():
     mult, bdiv = requant_constants(0.0407894998788833, ws, bias, 0.0422101989388465)
     m2, b2 = IO.requant_params(0.0407894998788833, ws.numpy(), bias.numpy(), 0.0422101989388465)
     assert np.array_equal(mult.numpy(), m2) and np.array_equal(bdiv.numpy(), b2)
+
+
+def test_input_lut_is_the_reference_pipeline_on_every_pixel_value():
+    """lut[c][v] == QuantStub(Normalize(ToTensor(v))) for all 3 x 256 inputs, via an actual image tensor."""
+    import torch
+    from convnet_quantization_b200 import synth
+    from convnet_quantization_b200.packing import input_lut
+    scale, zp = 0.0412, 59
+    lut = input_lut(scale, zp)
+    assert lut.shape == (3, 256) and lut.dtype == torch.uint8
+    img = torch.arange(256, dtype=torch.uint8).view(1, 1, 16, 16).expand(1, 3, 16, 16).contiguous()
+    q = torch.quantize_per_tensor(synth.normalize(img), scale, zp, torch.quint8).int_repr()
+    for c in range(3):
+        assert torch.equal(q[0, c].flatten(), lut[c])
+    # monotone in the pixel value, and the explicit-mean/std form agrees with the default
+    assert bool((lut[:, 1:].int() >= lut[:, :-1].int()).all())
+    assert torch.equal(input_lut(scale, zp, synth.CIFAR_MEAN, synth.CIFAR_STD), lut)
