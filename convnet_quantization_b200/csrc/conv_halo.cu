@@ -137,7 +137,7 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
       mbar_init(tmem_full_bar + i, 1);
       mbar_init(tmem_empty_bar + i, 4 * C::PARTS);  // the warps of the one set that drains this slot
     }
-    mbar_init(w_bar, 32);  // one cp.async-completion arrive per loader lane
+    mbar_init(w_bar, 32 * (HALO_EPI_WARPS + 1));  // one cp.async-completion arrive per copying thread
     *magic_smem = MAGIC_BITS;
     fence_barrier_init();
   }
@@ -182,22 +182,25 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
   __syncthreads();
   tc_fence_after();
 
+  if (warp <= HALO_LOAD_WARP) {
+    // Weights, once: global [COUT][9][CIN] -> nine [COUT][CIN] K-major swizzled tap blocks whose ROW n holds output
+    // channel epi_channel_of_column<NCH>(n) (the epilogue's thread <-> channel assignment, epilogue16.cuh).  All
+    // epilogue warps and the loader share the copy (up to 144 KB): with the loader alone it took several microseconds,
+    // which is most of what a small batch spends in this kernel.
+    constexpr int CPR = C::CIN / 16;  // 16-byte chunks per row
+    const uint32_t w_base = smem_u32(w_smem);
+    for (int g = threadIdx.x; g < 9 * COUT * CPR; g += 32 * (HALO_EPI_WARPS + 1)) {
+      const int part = g % CPR, n = (g / CPR) % COUT, tap = g / (CPR * COUT);
+      const int swz = (C::CIN == 64) ? ((n >> 1) & 3) : (n & 7);
+      const uint32_t dst = w_base + tap * C::W_TAP_BYTES + n * C::CIN + ((part ^ swz) << 4);
+      const int8_t* src = args.w + ((int64_t)epi_channel_of_column<C::NCH>(n) * 9 + tap) * C::CIN + part * 16;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(w_bar)) : "memory");
+  }
+
   if (warp == HALO_LOAD_WARP) {
     // ================================================================== loader warp
-    // Weights, once: global [COUT][9][CIN] -> nine [COUT][CIN] K-major swizzled tap blocks whose ROW n holds output
-    // channel epi_channel_of_column<NCH>(n) (the epilogue's thread <-> channel assignment, epilogue16.cuh).
-    {
-      constexpr int CPR = C::CIN / 16;  // 16-byte chunks per row
-      const uint32_t w_base = smem_u32(w_smem);
-      for (int g = lane; g < 9 * COUT * CPR; g += 32) {
-        const int part = g % CPR, n = (g / CPR) % COUT, tap = g / (CPR * COUT);
-        const int swz = (C::CIN == 64) ? ((n >> 1) & 3) : (n & 7);
-        const uint32_t dst = w_base + tap * C::W_TAP_BYTES + n * C::CIN + ((part ^ swz) << 4);
-        const int8_t* src = args.w + ((int64_t)epi_channel_of_column<C::NCH>(n) * 9 + tap) * C::CIN + part * 16;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-      }
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(w_bar)) : "memory");
-    }
     // 16-byte chunk g of an image: global offset g*16 (linear), pixel g/(CIN/16) = (h, w), part g%(CIN/16);
     // shared: position (h+1)*P + (w+1) of the image's slot, chunk slot part ^ swz(pos): address bits [7,9) (64-byte
     // rows) or [7,10) (128-byte rows) XORed into bits [4,..) - the hardware swizzle on absolute addresses (the buffers
