@@ -95,5 +95,5 @@ int encode_tensor_map(CUtensorMap* out, const void* gptr, int rank, const uint64
 }  // namespace b200q
 
 extern "C" const char* b200q_last_error(void) { return b200q::g_err; }
-extern "C" int b200q_abi_version(void) { return 2; }
+extern "C" int b200q_abi_version(void) { return 3; }  // 3: + b200q_conv12_fused, b200q_u8_conv3x3_first, b200q_static_forward_u8
 extern "C" uint64_t b200q_launch_count(void) { return b200q::g_launches.load(std::memory_order_relaxed); }

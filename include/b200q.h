@@ -59,7 +59,7 @@ typedef struct b200q_requant {
  * time and take the I2F/F2I form).  Without the flag the I2F/F2I form is always used. */
 #define B200Q_RQ_BOUNDED 1
 /* Caller guarantees |sum x*w| < 2^22 and |sum (x-zp_x)*w| < 2^22 for every possible uint8 input (a bound on the
- * layer's weights, see packing.acc_bound): lets the N=64 kernels skip the per-element run-time range test. */
+ * layer's weights, see packing.acc_bound): lets the tensor-core kernels skip the per-element run-time range test. */
 #define B200Q_RQ_ACC22 2
 
 /* 3x3 / stride 1 / pad 1 quantized convolution layer, packed.
@@ -162,15 +162,15 @@ int64_t b200q_static_workspace_bytes(int64_t b);
  * quant, conv1, conv2, pool1, conv3, conv4, pool2, conv5, conv6, pool3, fc1, fc2 (NHWC) for parity tests. */
 int b200q_static_forward(const b200q_static_net* net, const float* x, float* logits, int64_t b,
                          void* workspace, int64_t workspace_bytes, uint8_t* const* taps, void* stream);
+/* Same forward from raw uint8 NHWC pixels [b,32,32,3] (see b200q_u8_conv3x3_first for lut_host). */
+int b200q_static_forward_u8(const b200q_static_net* net, const uint8_t* x_nhwc, const uint8_t* lut_host, float* logits,
+                            int64_t b, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Measurement hook (bench.py roofline): the same forward with a CUDA event recorded on `stream` before every layer
  * kernel and after the last one; synchronises on the last event and writes b200q_static_num_stages() per-kernel
  * durations in milliseconds to stage_ms_host (HOST memory).  Stage i is named b200q_static_stage_name(i). */
 int b200q_static_num_stages(void);
 const char* b200q_static_stage_name(int i);
-/* Same forward from raw uint8 NHWC pixels [b,32,32,3] (see b200q_u8_conv3x3_first for lut_host). */
-int b200q_static_forward_u8(const b200q_static_net* net, const uint8_t* x_nhwc, const uint8_t* lut_host, float* logits,
-                            int64_t b, void* workspace, int64_t workspace_bytes, void* stream);
 int b200q_static_forward_profiled(const b200q_static_net* net, const float* x, float* logits, int64_t b,
                                   void* workspace, int64_t workspace_bytes, float* stage_ms_host, void* stream);
 
