@@ -170,6 +170,19 @@ def run_reference(args):
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit_line(obj) -> None:
+    """Write the one JSON line to the process's original stdout (see run_ours)."""
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def ncu_traffic(stage: str, batch: int):
     """DRAM bytes (read + written) per launch of `stage`, from the committed `ncu --set full` capture of one forward
     at the same batch (profiles/r01_ncu_net.json, written by scripts/ncu_summary.py); None when no capture matches."""
@@ -197,10 +210,14 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the quantized forward has no CPU fallback; use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # The contract is ONE JSON line on stdout.  NCCL prints its version banner on the C-level stdout when the first
+    # communicator is created, so everything but that line is routed to stderr: fd 1 is pointed at fd 2 for the whole
+    # run and the line is written to a private duplicate of the original stdout at the end (emit_line).
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL_DEBUG=VERSION makes NCCL print its banner on stdout, in front of the one JSON line the driver reads
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -277,7 +294,7 @@ def run_ours(args):
 
     if args.stages_only:  # kernel-timing experiments (scripts/gpu_debug_modes.sh): no e2e leg, no parity assertion
         if rank == 0:
-            print(json.dumps({"value": value, "ms_per_step": ms / args.steps, "roofline": roofline}), flush=True)
+            emit_line({"value": value, "ms_per_step": ms / args.steps, "roofline": roofline})
         return 0
 
     # ---- end to end through the reference-facing model object: pinned host input -> host logits
@@ -344,7 +361,7 @@ def run_ours(args):
             "clocks": clocks.summary(), "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "eval": {"top1": counts[0], "top5": counts[1], "total": counts[2]},
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
