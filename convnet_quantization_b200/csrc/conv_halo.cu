@@ -404,9 +404,10 @@ int conv3x3_halo_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_c
                           int* rc) {
   // needs the host mirrors of the per-channel constants (they become kernel parameters)
   if (!L->corr_host || !L->rq.mult_host || !L->rq.bdiv_host) return 1;
-  // Epilogue warps per layer (measured, same box): 16 warps x 8 channels win by ~2 % on the pooled layers (conv2,
-  // conv4), 8 warps x 16 channels by ~20 % on conv3, whose unpooled 128-channel tiles keep all 16 warps on the same tile
-  // and multiply the mbarrier wake-ups.  B200Q_HALO_EW=8|16 overrides (A-B timing only).
+  // Epilogue warps per layer: 8 warps x 16 channels everywhere.  16 warps x 8 channels (96 registers) were ~2 % ahead
+  // on the pooled layers before the epilogue constants were pinned in registers and ~20 % behind on conv3; with the
+  // current epilogue they are 0-2 % behind on all three (same box, interleaved runs).  B200Q_HALO_EW=8|16 overrides
+  // (A-B timing only).
   static int ew_env = -1;
   if (ew_env < 0) {
     const char* e = getenv("B200Q_HALO_EW");
@@ -416,7 +417,7 @@ int conv3x3_halo_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_c
   ((ew_env ? ew_env : EW_DEFAULT) == 16 ? launch_halo<IMG_, CIN_, COUT_, NBI_, POOL_, true, 16>(x, y, b, L, s) \
                                         : launch_halo<IMG_, CIN_, COUT_, NBI_, POOL_, true, 8>(x, y, b, L, s))
   if (L->img == 32 && L->cin == 64 && L->cout == 64) {
-    *rc = pool ? B200Q_HALO_CASE(32, 64, 64, 1, true, 16) : B200Q_HALO_CASE(32, 64, 64, 1, false, 8);
+    *rc = pool ? B200Q_HALO_CASE(32, 64, 64, 1, true, 8) : B200Q_HALO_CASE(32, 64, 64, 1, false, 8);
     return 0;
   }
   if (L->img == 16 && L->cin == 64 && L->cout == 128 && !pool) {
@@ -424,7 +425,7 @@ int conv3x3_halo_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_c
     return 0;
   }
   if (L->img == 16 && L->cin == 128 && L->cout == 128) {  // weights (144 KiB) + two single-image bands
-    *rc = pool ? B200Q_HALO_CASE(16, 128, 128, 1, true, 16) : B200Q_HALO_CASE(16, 128, 128, 1, false, 8);
+    *rc = pool ? B200Q_HALO_CASE(16, 128, 128, 1, true, 8) : B200Q_HALO_CASE(16, 128, 128, 1, false, 8);
     return 0;
   }
 #undef B200Q_HALO_CASE
