@@ -235,3 +235,27 @@ def test_conv_tc_many_bands_per_cta(qparams, qparams_np, name, b, pool):
     if pool:
         want = IO.max_pool2x2(want)
     assert np.array_equal(got[idx.numpy()], want)
+
+
+def test_alternate_instantiations_stay_bit_exact():
+    """The A-B switches select other template instantiations of the same kernels (16 epilogue warps x 8 channels in the
+    halo kernels, the fused conv1+conv2 kernel in the forward); they are read once per process, so they are exercised in
+    a child process: whole-net logits must equal the default configuration's bit for bit."""
+    import subprocess
+    import sys
+    code = (
+        "import torch, warnings; warnings.filterwarnings('ignore')\n"
+        "from convnet_quantization_b200 import synth\n"
+        "from convnet_quantization_b200.models.static_ptq_model import StaticPTQModel\n"
+        "m = StaticPTQModel(device='cuda'); m.fp32_model.load_state_dict(synth.make_state_dict(0)); q = m.quantize()\n"
+        "y = q.engine.forward(synth.images_f32(333, seed=77).cuda()); torch.cuda.synchronize()\n"
+        "import hashlib; print(hashlib.sha256(y.cpu().numpy().tobytes()).hexdigest())\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    for name, env in (("default", {}), ("ew16", {"B200Q_HALO_EW": "16"}), ("fuse12", {"B200Q_FUSE12": "1"})):
+        e = dict(os.environ)
+        e.update(env)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, cwd=root, timeout=600)
+        assert r.returncode == 0, f"{name}: {r.stderr[-1500:]}"
+        digests[name] = r.stdout.strip().splitlines()[-1]
+    assert digests["ew16"] == digests["default"] and digests["fuse12"] == digests["default"], digests
