@@ -153,34 +153,6 @@ __device__ __forceinline__ uint32_t requant4_prebiased(uint32_t v0, uint32_t v1,
   return pack_sat_u8(q1, q0, pack_sat_u8(q3, q2, 0u));
 }
 
-// 4*G channels of one pixel, pre-biased accumulators.  cm (int, MAGIC_BITS - corr) is only used by the exact fall-back.
-template <bool CHECK, int G>
-__device__ __forceinline__ void requant_chunk_prebiased(const uint32_t (&v)[4 * G], const int4* cm, const float4* k1,
-                                                        const float4* bd, const float4* mu, bool fast, int zp_out,
-                                                        int lo, uint32_t (&packed)[G]) {
-  const int zp_sub = zp_out - (int)MAGIC_BITS;
-  uint32_t bad = 0;
-  if (fast) {
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-      packed[g] = requant4_prebiased<CHECK>(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], k1[g], bd[g], mu[g],
-                                            zp_sub, lo, bad);
-  }
-  if (!fast || (CHECK && __any_sync(0xffffffffu, requant_magic_out_of_range(bad)))) {
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int4 c = cm[g];
-      const float4 b = bd[g], m = mu[g];
-      // v = raw + MAGIC_BITS, cm = MAGIC_BITS - corr  ->  raw - corr = v + cm - 2*MAGIC_BITS (wrapping arithmetic)
-      packed[g] = requant_u8((int)(v[4 * g + 0] + (uint32_t)c.x - 2u * MAGIC_BITS), b.x, m.x, zp_out, lo) |
-                  (requant_u8((int)(v[4 * g + 1] + (uint32_t)c.y - 2u * MAGIC_BITS), b.y, m.y, zp_out, lo) << 8) |
-                  (requant_u8((int)(v[4 * g + 2] + (uint32_t)c.z - 2u * MAGIC_BITS), b.z, m.z, zp_out, lo) << 16) |
-                  (requant_u8((int)(v[4 * g + 3] + (uint32_t)c.w - 2u * MAGIC_BITS), b.w, m.w, zp_out, lo) << 24);
-    }
-  }
-}
-
-
 // 32 consecutive output channels of one pixel (one tcgen05.ld 32x32b.x32 worth): v -> 8 packed words.
 // cm: this pixel's border-class row of (MAGIC_BITS - corr), bd/mu: bdiv / mult, all at the chunk's first channel
 // (shared memory, or register arrays after inlining).  `fast` = layer flagged B200Q_RQ_BOUNDED.
@@ -371,16 +343,6 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void tmem_st_fill8(uint32_t taddr, uint32_t value) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(value)
                : "memory");
-}
-// 32 lanes x 16 consecutive 32-bit columns.
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
 }
 // 16 lanes x 64 consecutive 32-bit columns in the mma-accumulator fragment layout (tools/probe_ld16.cu): register r
 // of thread t holds lane base_lane + t/4 + 8*((r>>1)&1), column col + 8*(r>>2) + 2*(t&3) + (r&1).  A thread therefore

@@ -158,66 +158,11 @@ __device__ __forceinline__ void epi_drain(uint32_t t_addr, EpiRegs<NCH>& K, uint
   release();
 }
 
-// ---------------------------------------------------------------------------------------------------- no pooling
-// One warp, one 32-lane quarter x 4*NCH columns of an accumulator slot.  t_addr = tmem base + (quarter*32 << 16) +
-// first column.  Thread (j = lane/4, q = lane&3) produces channels ch0..ch0+NCH-1 of four pixels: accumulator rows
-// 16*half + 8*s + j of the quarter (half, s in 0..1), stored at out + half*stride_half + s*stride_s.  In the halo
-// kernels' single-image blocks these are image rows 2*half + s of the quarter (stride_s = one image row); in
-// conv_pair.cu s selects the image of the pair and half the image row.  valid0/valid1: store the s = 0 / 1 pixels.
-// `release` is called (by all lanes, converged) once the slot has been read and re-armed.
-// SPLIT: read, re-arm and process one 16-lane half at a time (half the live registers; the slot is handed back after the
-// second half has been read) - for kernels whose warp count leaves less than ~150 registers per thread.
-template <bool CHECK, int NCH, bool SPLIT = false, class Consts, class Release>
-__device__ __forceinline__ void epi_block(uint32_t t_addr, EpiRegs<NCH>& K, const Consts& consts, int ch0, bool fast,
-                                          int zp_out, int lo, uint8_t* out, int64_t stride_s, int64_t stride_half,
-                                          bool valid0, bool valid1, Release release) {
-  constexpr int G = NCH / 4, PARTW = 4 * NCH;
-  const int zp_sub = zp_out - (int)MAGIC_BITS;
-  uint32_t v[2][2 * NCH];
-  if constexpr (!SPLIT) epi_drain<NCH>(t_addr, K, v, release);
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    if constexpr (SPLIT) {
-      const uint32_t a = t_addr + ((uint32_t)(16 * half) << 16);
-      tmem_ld_frag<PARTW / 8>(a, v[half]);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < PARTW; c += 16) tmem_st_fill_16x16(a + c, K.fill);
-      if (half == 1) {
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        release();
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {  // the thread's two pixels of this half: block rows 2*half + s
-      uint32_t packed[G];
-      uint32_t bad = 0;
-      if (fast) {
-        const uint32_t* w = v[half] + 2 * s;
-        packed[0] = epi_requant4<CHECK, 0>(w[0], w[1], w[4], w[5], K, zp_sub, lo, bad);
-        packed[1] = epi_requant4<CHECK, 4>(w[8], w[9], w[12], w[13], K, zp_sub, lo, bad);
-        if constexpr (G == 4) {
-          packed[2] = epi_requant4<CHECK, 8>(w[16], w[17], w[20], w[21], K, zp_sub, lo, bad);
-          packed[3] = epi_requant4<CHECK, 12>(w[24], w[25], w[28], w[29], K, zp_sub, lo, bad);
-        }
-      }
-      if (!fast || (CHECK && __any_sync(0xffffffffu, requant_magic_out_of_range(bad)))) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const uint32_t* w = v[half] + 8 * g + 2 * s;
-          packed[g] = epi_requant4_exact(w[0], w[1], w[4], w[5], consts, ch0 + 4 * g, zp_out, lo);
-        }
-      }
-      if (s == 0 ? valid0 : valid1) epi_store<G>(out + half * stride_half + s * stride_s, packed);
-    }
-  }
-}
-
 // ------------------------------------------------------------------- low-register variants (conv12_fused.cu)
-// Same arithmetic as epi_block<SPLIT> / epi_block_pool for 16 channels per thread, shaped for a 128-register budget
-// and for a caller-supplied store: `store(half, s, packed)` receives the 16 bytes of pixel (half, s) of the thread.
+// Same arithmetic as epi_pipeline / epi_block_pool for 16 channels per thread, shaped for a 128-register budget: one
+// 16-lane half at a time (read, re-arm, requantise), slot handed back after the second half has been read, and a
+// caller-supplied store: `store(half, s, packed)` receives the 16 bytes of the thread's pixel at accumulator row
+// 16*half + 8*s + lane/4 of the quarter.
 template <bool CHECK, class Consts, class Store, class Release>
 __device__ __forceinline__ void epi_block_store16(uint32_t t_addr, EpiRegs<16>& K, const Consts& consts, int ch0, bool fast,
                                                   int zp_out, int lo, Store store, Release release) {
@@ -320,12 +265,17 @@ __device__ __forceinline__ void epi_block_pool16_units(uint32_t t_addr, EpiRegs<
 // store in lock-step).  Here a warp keeps one 16-lane half in flight while it computes the other: the tcgen05.ld of
 // half 1 is issued before the arithmetic of half 0, and the first half of the NEXT tile before the arithmetic of
 // half 1.  `next(EpiTile&)` yields the warp's tiles in order (false when there are none left).
+// A tile of the warp is one 32-lane quarter x 4*NCH columns of an accumulator slot.  Thread (j = lane/4, q = lane&3)
+// produces channels ch0..ch0+NCH-1 of four pixels: accumulator rows 16*half + 8*s + j of the quarter (half, s in 0..1),
+// stored at out + half*stride_half + s*stride_s.  In the halo kernels' single-image blocks these are image rows
+// 2*half + s of the quarter (stride_s = one image row); in conv_pair.cu s selects the image of the pair and half the
+// image row.  valid0/valid1: store the s = 0 / 1 pixels.
 struct EpiTile {
   uint32_t t_addr;        // tmem base + (quarter*32 << 16) + first column of the warp's part
   uint64_t* full_bar;     // accumulator complete (MMA commit)
   uint64_t* empty_bar;    // slot drained (one arrive per epilogue warp)
   uint32_t parity;        // phase parity of full_bar for this tile
-  uint8_t* out;           // see epi_block
+  uint8_t* out;           // address of the thread's pixel (half 0, s 0), channel ch0; see epi_pipeline
   bool valid0, valid1;
 };
 
