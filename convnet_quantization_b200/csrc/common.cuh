@@ -19,6 +19,9 @@ int launched(const char* what);  // after every <<<>>>: bumps b200q_launch_count
 #define B200Q_CUDA(expr) do { int _rc = ::b200q::check_cuda((expr), #expr); if (_rc) return _rc; } while (0)
 #define B200Q_REQUIRE(cond, ...) do { if (!(cond)) { ::b200q::set_error(__VA_ARGS__); return B200Q_ERR_INVALID_ARG; } } while (0)
 int num_sms();
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: `mask` (one static per kernel instantiation)
+// remembers on which devices of this process it has been raised for `kernel`.
+int ensure_dynamic_smem(const void* kernel, int bytes, uint64_t* mask);
 // conv_halo.cu: halo-resident kernel for the cin=64 layers; returns 1 when the geometry is not covered
 // conv1_tc.cu: tensor-core first layer (fused quantize); returns 1 when the layer cannot take that path
 int conv1_tc_dispatch(const float* x, uint8_t* y, int64_t b, float inv_scale, const b200q_conv3x3* L, cudaStream_t s,

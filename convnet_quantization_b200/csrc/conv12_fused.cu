@@ -441,12 +441,9 @@ extern "C" int b200q_conv12_fused(const float* x, uint8_t* y, int64_t b, float i
   void (*kernel)(F12Consts, F12Args) =
       check1 ? (check2 ? conv12_fused_kernel<true, true> : conv12_fused_kernel<true, false>)
              : (check2 ? conv12_fused_kernel<false, true> : conv12_fused_kernel<false, false>);
-  static bool attr_set[4] = {false, false, false, false};
+  static uint64_t attr_mask[4] = {0, 0, 0, 0};
   const int idx = (check1 ? 2 : 0) + (check2 ? 1 : 0);
-  if (!attr_set[idx]) {
-    B200Q_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f12::SMEM));
-    attr_set[idx] = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), f12::SMEM, &attr_mask[idx])) return rc;
   const int grid = b < num_sms() ? (int)b : num_sms();
   kernel<<<grid, f12::THREADS, f12::SMEM, (cudaStream_t)stream>>>(consts, args);
   return launched("conv12_fused_kernel");

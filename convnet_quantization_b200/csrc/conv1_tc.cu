@@ -311,14 +311,10 @@ static int conv1_tc_launch(const float* x, const uint8_t* xu8, const uint8_t* lu
   void (*kernel)(C1Consts, C1Lut, C1Args) =
       u8in ? (check ? conv1_tc_kernel<true, true> : conv1_tc_kernel<false, true>)
            : (check ? conv1_tc_kernel<true, false> : conv1_tc_kernel<false, false>);
-  static bool attr_set[4] = {false, false, false, false};
+  static uint64_t attr_mask[4] = {0, 0, 0, 0};
   const int idx = (u8in ? 2 : 0) + (check ? 1 : 0);
-  if (!attr_set[idx]) {
-    *rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM),
-                     "cudaFuncSetAttribute(conv1_tc_kernel)");
-    if (*rc) return 0;
-    attr_set[idx] = true;
-  }
+  *rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), C1_SMEM, &attr_mask[idx]);
+  if (*rc) return 0;
   C1Args args{x, xu8, y, L->w, b, inv_scale, L->zp_x, rq.zp_out, rq.relu ? rq.zp_out : 0, 1};
   const int grid = b < num_sms() ? (int)b : num_sms();
   kernel<<<grid, C1_THREADS, C1_SMEM, s>>>(consts, lut, args);

@@ -377,11 +377,8 @@ static int launch_halo(const uint8_t* x, uint8_t* y, int64_t n_img, const b200q_
     consts.mult[c] = rq.mult_host[c];
   }
   auto kernel = conv_halo_kernel<IMG, CIN, COUT, NBI, POOL, CHECK, EW>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200Q_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  static uint64_t attr_mask = 0;  // per template instantiation
+  if (int arc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), C::SMEM_BYTES, &attr_mask)) return arc;
   const int num_bands = (int)((n_img + NBI - 1) / NBI);
   static int debug = -1;
   if (debug < 0) {

@@ -367,11 +367,8 @@ static int launch_tc(const uint8_t* x, uint8_t* y, int64_t m_rows, const int8_t*
       return launch_tc<IMG, CIN, COUT, B_RESIDENT, POOL, false>(x, y, m_rows, w, corr, rq, stream);
   }
   auto kernel = igemm_tc_kernel<IMG, CIN, COUT, B_RESIDENT, POOL, CHECK>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    B200Q_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  static uint64_t attr_mask = 0;  // per template instantiation
+  if (int arc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), C::SMEM_BYTES, &attr_mask)) return arc;
   TcArgs args{y, rq.mult, rq.bdiv, corr, m_rows, num_m_tiles, rq.zp_out, rq.relu ? rq.zp_out : 0,
               (rq.flags & B200Q_RQ_BOUNDED) ? 1 : 0};
   const int num_tiles = num_m_tiles * C::N_TILES;

@@ -43,6 +43,19 @@ int num_sms() {
   return cached[dev];
 }
 
+int ensure_dynamic_smem(const void* kernel, int bytes, uint64_t* mask) {
+  int dev = 0;
+  int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+  if (rc) return rc;
+  const uint64_t bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0;  // devices >= 64: set the attribute on every launch
+  if (bit && (*mask & bit)) return 0;
+  rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes),
+                  "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+  if (rc) return rc;
+  *mask |= bit;
+  return 0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

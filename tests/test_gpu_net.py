@@ -106,3 +106,20 @@ def test_uint8_data_path_host_pipeline(golden_qparams):
     got = net.forward_uint8(pix)
     assert not got.is_cuda and torch.equal(got, want)
     assert torch.equal(net.forward_uint8(pix.cuda()).cpu(), want)
+
+
+def test_second_device_in_the_same_process(golden_qparams):
+    """One process, two GPUs (``model.to('cuda:1')`` in the drop-in API): per-device kernel attributes (opt-in shared
+    memory size) and workspaces must follow the device; logits are bit-identical on both."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    from convnet_quantization_b200 import synth
+    from convnet_quantization_b200.engine import StaticEngine
+    x = synth.images_f32(200, seed=21)
+    e0 = StaticEngine(golden_qparams, "cuda:0")
+    y0 = e0.forward(x.to("cuda:0")).cpu()
+    e1 = StaticEngine(golden_qparams, "cuda:1")
+    with torch.cuda.device(1):
+        y1 = e1.forward(x.to("cuda:1")).cpu()
+    y0b = e0.forward(x.to("cuda:0")).cpu()
+    assert torch.equal(y0, y1) and torch.equal(y0, y0b)
