@@ -16,6 +16,12 @@ namespace b200q {
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int launched(const char* what);  // after every <<<>>>: bumps b200q_launch_count(), returns the launch status
+// Programmatic dependent launch (net.cu b200q_graph_create): while set on the calling thread, launch_kernel() marks
+// every kernel "programmatic stream serialization allowed", i.e. it may START while its predecessor in the stream still
+// runs; the kernel orders its dependent memory accesses itself with pdl_wait() (below).
+void note_graph_replay(int kernels);  // a CUDA-graph replay launched `kernels` kernels (b200q_launch_count)
+bool pdl_enabled();
+void pdl_set(bool on);
 #define B200Q_CUDA(expr) do { int _rc = ::b200q::check_cuda((expr), #expr); if (_rc) return _rc; } while (0)
 #define B200Q_REQUIRE(cond, ...) do { if (!(cond)) { ::b200q::set_error(__VA_ARGS__); return B200Q_ERR_INVALID_ARG; } } while (0)
 int num_sms();
@@ -31,6 +37,39 @@ int conv3x3_halo_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_c
 // conv_pair.cu: pair-interleaved halo kernel for the 8x8 layers (conv5, conv6); returns 1 when not covered
 int conv3x3_pair_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, bool pool, cudaStream_t s,
                           int* rc);
+
+// One launch site for the forward's kernels: <<<>>> semantics plus the PDL attribute when pdl_enabled().
+template <class... KArgs, class... Args>
+int launch_kernel(const char* what, void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s,
+                  Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return check_cuda(e, what);
+  }
+  return launched(what);
+}
+
+// ---------------------------------------------------------------- programmatic dependent launch (device side)
+// pdl_launch_dependents(): this CTA no longer holds back the launch of the next kernel in the stream (which then runs
+// its prologue - barrier init, TMEM allocation, weights into shared memory - on whatever SMs are free).
+// pdl_wait(): returns once the preceding kernel has completed and its memory is visible; executed by the thread(s) that
+// issue the first access to memory the predecessor writes (or reads, for buffers this kernel overwrites: every store of a
+// layer kernel is data-dependent on its loader's reads).  Both are no-ops in a launch without the PDL attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---------------------------------------------------------------- exact fbgemm requantisation
 // t = f32(acc) + bdiv; t = t * mult; q = clamp(rne(t) + zp, lo, 255).  Intrinsics forbid FMA contraction

@@ -90,6 +90,7 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t zp4 = (uint32_t)args.zp_x * 0x01010101u;
+  pdl_launch_dependents();
 
   if (warp == C1_PROD_WARP0 && lane == 0) {
     *magic_smem = MAGIC_BITS;
@@ -175,6 +176,7 @@ conv1_tc_kernel(const __grid_constant__ C1Consts consts, const __grid_constant__
         }
       }
     };
+    pdl_wait();  // first access to memory another kernel of the stream may own
     if (my_imgs > 0) load_image(0);
     for (int it = 0; it < my_imgs; ++it) {
       const int buf = it & 1;
@@ -317,8 +319,7 @@ static int conv1_tc_launch(const float* x, const uint8_t* xu8, const uint8_t* lu
   if (*rc) return 0;
   C1Args args{x, xu8, y, L->w, b, inv_scale, L->zp_x, rq.zp_out, rq.relu ? rq.zp_out : 0, 1};
   const int grid = b < num_sms() ? (int)b : num_sms();
-  kernel<<<grid, C1_THREADS, C1_SMEM, s>>>(consts, lut, args);
-  *rc = launched("conv1_tc_kernel");
+  *rc = launch_kernel("conv1_tc_kernel", kernel, grid, C1_THREADS, C1_SMEM, s, consts, lut, args);
   return 0;
 }
 

@@ -91,11 +91,18 @@ struct HaloArgs {
   int zp_x;            // activation zero-point held by the pad positions
   int zp_out, lo;
   int bounded;
-  int debug;           // B200Q_HALO_DEBUG bits (timing experiments only; results are wrong when set):
-                       //   2 = MMA issuer skips the MMAs, 4 = loader skips the band copies,
+  int debug;           // B200Q_HALO_DEBUG bits, honoured only by -DB200Q_DEV builds (timing experiments; results are
+                       // wrong when set): 2 = MMA issuer skips the MMAs, 4 = loader skips the band copies,
                        //   8 = epilogue only drains (no arithmetic, no stores),
                        //   16 = block 0 prints its SM-clock cycles and wall nanoseconds (effective SM clock under load)
 };
+// The role-disabling switches exist in development builds only: the product library compiles them out, so no inherited
+// environment variable can break bit-exactness.
+#ifdef B200Q_DEV
+#define HALO_DBG(bit) ((args.debug & (bit)) != 0)
+#else
+#define HALO_DBG(bit) false
+#endif
 
 // Per-output-channel constants, passed by value as a kernel parameter (constant bank).
 template <int COUT>
@@ -127,6 +134,7 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
   const int lane = threadIdx.x & 31;
   const long long dbg_c0 = clock64();
   const uint64_t dbg_t0 = globaltimer_ns();
+  pdl_launch_dependents();
 
   if (warp == HALO_LOAD_WARP && lane == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -206,6 +214,7 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
     // rows) or [7,10) (128-byte rows) XORed into bits [4,..) - the hardware swizzle on absolute addresses (the buffers
     // are 1 KiB aligned)
     constexpr int CHUNKS_PER_IMG = IMG * IMG * (C::CIN / 16);
+    pdl_wait();  // the activations are the previous kernel's output (the weight copy above did not need it)
     int it = 0;
     for (int band = blockIdx.x; band < args.num_bands; band += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -213,7 +222,7 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
       const uint32_t a_buf = smem_u32(a_smem + buf * C::A_BYTES);
       for (int bi = 0; bi < NBI; ++bi) {
         const int64_t img = (int64_t)band * NBI + bi;
-        if (img >= args.n_img || (args.debug & 4)) break;  // stale data: those pixels are never stored
+        if (img >= args.n_img || HALO_DBG(4)) break;  // stale data: those pixels are never stored
         const uint8_t* src = args.x + img * (int64_t)(IMG * IMG * C::CIN);
 #pragma unroll 8
         for (int g = lane; g < CHUNKS_PER_IMG; g += 32) {
@@ -259,7 +268,7 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
           const uint64_t a_tile = a_desc0 + (uint64_t)(((bi * C::POS_PER_IMG + r0 * C::P + c0) * C::CIN) >> 4);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            if (args.debug & 2) break;
+            if (HALO_DBG(2)) break;
 #pragma unroll
             for (int k = 0; k < C::CIN / 32; ++k) {
               const uint64_t da = a_tile + (uint64_t)((((tap / 3) * C::P + (tap % 3)) * C::CIN + k * 32) >> 4);
@@ -285,7 +294,7 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
     EpiRegs<C::NCH> K;
     epi_init(consts, ch0, magic_smem, K);
     if constexpr (!POOL) {
-      if (!(args.debug & 8)) {
+      if (!HALO_DBG(8)) {
         // software-pipelined over the warp's tiles (epilogue16.cuh epi_pipeline)
         int band = blockIdx.x, acc_base = 0;
         int t = (set - acc_base % C::SETS + C::SETS) % C::SETS;
@@ -314,7 +323,7 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
                             next);
       }
     }
-    if (POOL || (args.debug & 8)) {
+    if (POOL || HALO_DBG(8)) {
       int acc_base = 0;
       for (int band = blockIdx.x; band < args.num_bands; band += gridDim.x, acc_base += C::TILES) {
         // first tile of this band that belongs to the set: acc_it = acc_base + t  with  acc_it % SETS == set
@@ -331,7 +340,7 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
           };
           mbar_wait(tmem_full_bar + slot, (acc_it / HALO_SLOTS) & 1);
           tc_fence_after();
-          if (args.debug & 8) {
+          if (HALO_DBG(8)) {
             tc_fence_before();
             __syncwarp();
             release();
@@ -348,7 +357,7 @@ conv_halo_kernel(const __grid_constant__ HaloConsts<COUT> consts, const HaloArgs
 
   tc_fence_before();
   __syncthreads();
-  if ((args.debug & 16) && blockIdx.x == 0 && threadIdx.x == 0) {
+  if (HALO_DBG(16) && blockIdx.x == 0 && threadIdx.x == 0) {
     const long long dc = clock64() - dbg_c0;
     const uint64_t dt = globaltimer_ns() - dbg_t0;
     printf("conv_halo<%d,%d,%d> block 0: %lld cycles in %llu ns = %.0f MHz\n", IMG, CIN, COUT, dc, (unsigned long long)dt,
@@ -380,11 +389,15 @@ static int launch_halo(const uint8_t* x, uint8_t* y, int64_t n_img, const b200q_
   static uint64_t attr_mask = 0;  // per template instantiation
   if (int arc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), C::SMEM_BYTES, &attr_mask)) return arc;
   const int num_bands = (int)((n_img + NBI - 1) / NBI);
+#ifdef B200Q_DEV
   static int debug = -1;
   if (debug < 0) {
     const char* e = getenv("B200Q_HALO_DEBUG");
     debug = e ? atoi(e) : 0;
   }
+#else
+  const int debug = 0;
+#endif
   HaloArgs args{x,        y,
                 L->w,     n_img,
                 num_bands, L->zp_x,
@@ -392,8 +405,7 @@ static int launch_halo(const uint8_t* x, uint8_t* y, int64_t n_img, const b200q_
                 (rq.flags & B200Q_RQ_BOUNDED) ? 1 : 0,
                 debug};
   const int grid = num_bands < num_sms() ? num_bands : num_sms();
-  kernel<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(consts, args);
-  return launched("conv_halo_kernel");
+  return launch_kernel("conv_halo_kernel", kernel, grid, C::THREADS, C::SMEM_BYTES, stream, consts, args);
 }
 
 // Entry used by b200q_conv3x3_tc for the geometries this kernel covers; returns 1 when the geometry is not handled.
@@ -404,7 +416,8 @@ int conv3x3_halo_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_c
   // Epilogue warps per layer: 8 warps x 16 channels everywhere.  16 warps x 8 channels (96 registers) were ~2 % ahead
   // on the pooled layers before the epilogue constants were pinned in registers and ~20 % behind on conv3; with the
   // current epilogue they are 0-2 % behind on all three (same box, interleaved runs).  B200Q_HALO_EW=8|16 overrides
-  // (A-B timing only).
+  // in -DB200Q_DEV builds (A-B timing only).
+#ifdef B200Q_DEV
   static int ew_env = -1;
   if (ew_env < 0) {
     const char* e = getenv("B200Q_HALO_EW");
@@ -413,6 +426,10 @@ int conv3x3_halo_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_c
 #define B200Q_HALO_CASE(IMG_, CIN_, COUT_, NBI_, POOL_, EW_DEFAULT)                                      \
   ((ew_env ? ew_env : EW_DEFAULT) == 16 ? launch_halo<IMG_, CIN_, COUT_, NBI_, POOL_, true, 16>(x, y, b, L, s) \
                                         : launch_halo<IMG_, CIN_, COUT_, NBI_, POOL_, true, 8>(x, y, b, L, s))
+#else  // product build: the one measured-best instantiation per layer, no environment switch
+#define B200Q_HALO_CASE(IMG_, CIN_, COUT_, NBI_, POOL_, EW_DEFAULT) \
+  launch_halo<IMG_, CIN_, COUT_, NBI_, POOL_, true, EW_DEFAULT>(x, y, b, L, s)
+#endif
   if (L->img == 32 && L->cin == 64 && L->cout == 64) {
     *rc = pool ? B200Q_HALO_CASE(32, 64, 64, 1, true, 8) : B200Q_HALO_CASE(32, 64, 64, 1, false, 8);
     return 0;

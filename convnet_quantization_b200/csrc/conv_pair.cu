@@ -60,9 +60,14 @@ struct PairArgs {
   int64_t n_img;
   int num_bands;
   int zp_x, zp_out, lo, bounded;
-  int debug;  // B200Q_PAIR_DEBUG bits (timing experiments only; results are wrong when set): 2 = no MMAs, 4 = no
-              // activation copies, 8 = epilogue only drains, 32 = no weight TMA
+  int debug;  // B200Q_PAIR_DEBUG bits, honoured only by -DB200Q_DEV builds (timing experiments; results are wrong when
+              // set): 2 = no MMAs, 4 = no activation copies, 8 = epilogue only drains, 32 = no weight TMA
 };
+#ifdef B200Q_DEV
+#define PAIR_DBG(bit) ((args.debug & (bit)) != 0)
+#else
+#define PAIR_DBG(bit) false  // compiled out of the product library
+#endif
 
 struct alignas(16) PairConsts {  // the CTA's 128 output channels are [128*half, 128*half + 128)
   int32_t cm[PAIR_COUT];
@@ -104,6 +109,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int nhalf = blockIdx.x & 1;                         // which 128 output channels
   const int band0 = blockIdx.x >> 1, band_step = gridDim.x >> 1;
+  pdl_launch_dependents();
 
   if (warp == PAIR_W_WARP && lane == 0) {
     tma_prefetch_desc(&map_w);
@@ -167,6 +173,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
     const int part = lane % CPR;
     const int w_it = (lane / CPR) % IMG, w_step = 32 / CPR;                // KC = 128: w = lane/8 + 4*iteration
     const int h_it = lane / (IMG * CPR);                                   // KC = 64 only: 0 (32 lanes = one row)
+    pdl_wait();  // the activations are the previous kernel's output
     int it = 0;
     for (int band = band0; band < args.num_bands; band += band_step, ++it) {
       for (int kh = 0; kh < C::KH; ++kh) {
@@ -175,7 +182,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
         const uint32_t a_buf = smem_u32(a_smem + ab * C::A_BYTES);
         for (int bi = 0; bi < 2 * PAIR_T; ++bi) {
           const int64_t img = (int64_t)band * (2 * PAIR_T) + bi;
-          if (img >= args.n_img || (args.debug & 4)) break;  // stale data: those pixels are never stored
+          if (img >= args.n_img || PAIR_DBG(4)) break;  // stale data: those pixels are never stored
           const uint8_t* src = args.x + img * (int64_t)(IMG * IMG * CIN) + kh * C::KC + part * 16;
           const int pos0 = (bi >> 1) * C::PAIR_POS + (bi & 1) * (IMG + 1) + C::P + 1;  // pixel (0, 0)
 #pragma unroll
@@ -199,7 +206,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
         for (int j = 0; j < C::CHUNKS; ++j) {
           const int kh = j / 9, tap = j % 9;
           mbar_wait(b_empty + stage, phase ^ 1);
-          if (args.debug & 32) {
+          if (PAIR_DBG(32)) {
             mbar_arrive(b_full + stage);
             if (++stage == C::STAGES) {
               stage = 0;
@@ -252,7 +259,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
             const uint64_t db0 = b_desc0 + (uint64_t)((stage * C::B_BYTES) >> 4);
 #pragma unroll
             for (int k = 0; k < C::MMAS_PER_CHUNK; ++k)
-              if (!(args.debug & 2)) tc_mma_i8(d_tmem, da0 + (uint64_t)((k * 32) >> 4), db0 + (uint64_t)((k * 32) >> 4), idesc, 1u);
+              if (!PAIR_DBG(2)) tc_mma_i8(d_tmem, da0 + (uint64_t)((k * 32) >> 4), db0 + (uint64_t)((k * 32) >> 4), idesc, 1u);
             tc_commit(b_empty + stage);  // chunk reusable once both issuers' MMAs have read it
           }
           __syncwarp();
@@ -278,7 +285,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
     EpiRegs<PAIR_NCH> K;
     epi_init(consts, ch0, magic_smem, K);
     if constexpr (!POOL) {
-      if (!(args.debug & 8)) {
+      if (!PAIR_DBG(8)) {
         // software-pipelined over the warp's tiles (epilogue16.cuh epi_pipeline); accumulator row 16*half + 8*s + j of
         // the quarter = pixel (2*quarter + half, j) of image s of the pair
         int band = band0, t = 0, acc_it = 0;
@@ -305,7 +312,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
                             next);
       }
     }
-    if (POOL || (args.debug & 8)) {
+    if (POOL || PAIR_DBG(8)) {
       int acc_it = 0;
       for (int band = band0; band < args.num_bands; band += band_step) {
         for (int t = 0; t < PAIR_T; ++t, ++acc_it) {
@@ -317,7 +324,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
           };
           mbar_wait(tmem_full_bar + slot, (acc_it / PAIR_SLOTS) & 1);
           tc_fence_after();
-          if (args.debug & 8) {
+          if (PAIR_DBG(8)) {
             tc_fence_before();
             __syncwarp();
             release();
@@ -374,11 +381,15 @@ static int launch_pair(const uint8_t* x, uint8_t* y, int64_t n_img, const b200q_
   static uint64_t attr_mask = 0;  // per template instantiation
   if (int arc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), C::SMEM_BYTES, &attr_mask)) return arc;
   const int num_bands = (int)((n_img + 2 * PAIR_T - 1) / (2 * PAIR_T));
+#ifdef B200Q_DEV
   static int debug = -1;
   if (debug < 0) {
     const char* e = getenv("B200Q_PAIR_DEBUG");
     debug = e ? atoi(e) : 0;
   }
+#else
+  const int debug = 0;
+#endif
   PairArgs args{x,         y,
                 n_img,     num_bands,
                 L->zp_x,   rq.zp_out,
@@ -386,8 +397,7 @@ static int launch_pair(const uint8_t* x, uint8_t* y, int64_t n_img, const b200q_
                 debug};
   // two CTAs (one per channel half) per band; an even grid no larger than the SM count
   int grid = 2 * num_bands < num_sms() ? 2 * num_bands : (num_sms() & ~1);
-  kernel<<<grid, PAIR_THREADS, C::SMEM_BYTES, stream>>>(map_w, consts, args);
-  return launched("conv_pair_kernel");
+  return launch_kernel("conv_pair_kernel", kernel, grid, PAIR_THREADS, C::SMEM_BYTES, stream, map_w, consts, args);
 }
 
 // Entry used by b200q_conv3x3_tc for the geometries this kernel covers; returns 1 when the geometry is not handled.

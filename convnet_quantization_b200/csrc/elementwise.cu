@@ -63,7 +63,7 @@ __global__ void quantize_nchw_to_nhwc_generic_kernel(const float* __restrict__ x
 }
 
 // Flat quantize: 16 floats in (4 x float4), 16 bytes out per thread-iteration.
-// qp (optional, device): {min, max, scale, inv_scale, zp-as-float} produced by minmax_kernel — used by linear_dynamic.
+// qp (optional, device): {min, max, scale, inv_scale, zp-as-float} produced by minmax_kernel.
 __global__ void __launch_bounds__(256) quantize_flat_kernel(const float* __restrict__ x, uint8_t* __restrict__ y,
                                                             int64_t n, float inv_scale, int zp,
                                                             const float* __restrict__ qp) {
@@ -161,19 +161,38 @@ __global__ void __launch_bounds__(256) max_pool2x2_nhwc_kernel(const uint4* __re
 // out[4]=zero-point (as float), mirroring ChooseQuantizationParams as reached by quantized::linear_dynamic.
 constexpr int MINMAX_MAX_BLOCKS = 1024;
 
+// Port of ChooseQuantizationParams (ATen/native/quantized/cpu/QuantUtils.h) as quantized::linear_dynamic reaches it:
+// qmin = 0, qmax = 255, reduce_range = true (-> 0..127), preserve_sparsity = false.  Double intermediates, the tests on
+// float(scale), the SMALL_SCALE_THRESHOLD cut-off with its min/max rescaling and the "smaller error terms" choice
+// between the two zero-point candidates follow the original step by step.
 __device__ __forceinline__ void choose_qparams_reduce_range(float mn, float mx, float* out) {
   const int qmin = 0, qmax = 127;
-  double dmn = fmin((double)mn, 0.0), dmx = fmax((double)mx, 0.0);
-  double scale = (dmx - dmn) / (double)(qmax - qmin);
-  if ((float)scale == 0.0f || isinf(1.0 / scale)) scale = 0.1;
-  const double zp_from_min = qmin - dmn / scale;
-  const double zp_from_max = qmax - dmx / scale;
-  const double err_min = fabs((double)qmin) + fabs(dmn / scale);
-  const double err_max = fabs((double)qmax) + fabs(dmx / scale);
+  constexpr float SMALL_SCALE_THRESHOLD = 6.1e-5f;
+  mn = fminf(mn, 0.f);
+  mx = fmaxf(mx, 0.f);
+  double scale = ((double)mx - (double)mn) / (double)(qmax - qmin);
+  if ((float)scale == 0.0f || isinf(__fdiv_rn(1.0f, (float)scale))) scale = 0.1;
+  if (scale < (double)SMALL_SCALE_THRESHOLD) {
+    const float org_scale = (float)scale;
+    scale = (double)SMALL_SCALE_THRESHOLD;
+    if (mn == 0.0f) {
+      mx = __fmul_rn(SMALL_SCALE_THRESHOLD, (float)(qmax - qmin));
+    } else if (mx == 0.0f) {
+      mn = -__fmul_rn(SMALL_SCALE_THRESHOLD, (float)(qmax - qmin));
+    } else {
+      const float amplifier = __fdiv_rn(SMALL_SCALE_THRESHOLD, org_scale);
+      mn = __fmul_rn(mn, amplifier);
+      mx = __fmul_rn(mx, amplifier);
+    }
+  }
+  const double zp_from_min = (double)qmin - (double)mn / scale;
+  const double zp_from_max = (double)qmax - (double)mx / scale;
+  const double err_min = fabs((double)qmin) - fabs((double)mn / scale);
+  const double err_max = fabs((double)qmax) - fabs((double)mx / scale);
   const double izp = err_min < err_max ? zp_from_min : zp_from_max;
   int zp;
-  if (izp < qmin) zp = qmin;
-  else if (izp > qmax) zp = qmax;
+  if (izp < (double)qmin) zp = qmin;
+  else if (izp > (double)qmax) zp = qmax;
   else zp = (int)nearbyint(izp);
   const float s = (float)scale;
   out[2] = s;
@@ -181,9 +200,12 @@ __device__ __forceinline__ void choose_qparams_reduce_range(float mn, float mx, 
   out[4] = (float)zp;
 }
 
+// DYNAMIC = true: quantized::linear_dynamic's range (always contains 0) + its qparams; false: plain torch.aminmax.
+template <bool DYNAMIC>
 __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out,
                                                      float* __restrict__ partial, unsigned int* __restrict__ counter) {
-  float mn = 0.0f, mx = 0.0f;  // range always includes 0 (fbgemm: min(x,0), max(x,0))
+  const float MN0 = DYNAMIC ? 0.0f : __int_as_float(0x7f800000), MX0 = DYNAMIC ? 0.0f : __int_as_float(0xff800000);
+  float mn = MN0, mx = MX0;  // DYNAMIC: range always includes 0 (fbgemm: min(x,0), max(x,0))
   const int64_t nvec = n / 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
@@ -223,8 +245,8 @@ __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ x
   __syncthreads();
   if (is_last) {
     __threadfence();
-    mn = 0.0f;
-    mx = 0.0f;
+    mn = MN0;
+    mx = MX0;
     for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
       mn = fminf(mn, __ldcg(partial + i));
       mx = fmaxf(mx, __ldcg(partial + MINMAX_MAX_BLOCKS + i));
@@ -247,19 +269,88 @@ __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ x
       }
       out[0] = mn;
       out[1] = mx;
-      choose_qparams_reduce_range(mn, mx, out);
+      if constexpr (DYNAMIC) choose_qparams_reduce_range(mn, mx, out);
       *counter = 0;  // ready for the next call on this stream
     }
   }
 }
 
-int launch_minmax(const float* x, int64_t n, float* out5, void* scratch, cudaStream_t s) {
+int launch_minmax(const float* x, int64_t n, float* out5, void* scratch, cudaStream_t s, bool dynamic) {
   float* partial = reinterpret_cast<float*>(scratch);
   unsigned int* counter = reinterpret_cast<unsigned int*>(partial + 2 * MINMAX_MAX_BLOCKS);
   int blocks = grid_for(n / 4 + 1, 256, 4);
   if (blocks > MINMAX_MAX_BLOCKS) blocks = MINMAX_MAX_BLOCKS;
-  minmax_kernel<<<blocks, 256, 0, s>>>(x, n, out5, partial, counter);
+  if (dynamic)
+    minmax_kernel<true><<<blocks, 256, 0, s>>>(x, n, out5, partial, counter);
+  else
+    minmax_kernel<false><<<blocks, 256, 0, s>>>(x, n, out5, partial, counter);
   return launched("minmax_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// torch.histc for the calibration observers: per-block shared-memory histogram (32-bit counts, shared atomics), flushed
+// with one 64-bit global atomic per non-empty bin.  The bin of an element is ATen's CPU rule evaluated in fp32 with the
+// same operation order: int(((x - lo) * bins) / (hi - lo)).
+constexpr int HISTC_MAX_BINS = 4096;
+__global__ void __launch_bounds__(256) histc_kernel(const float* __restrict__ x, int64_t n, float lo, float hi, int bins,
+                                                    unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int s_hist[HISTC_MAX_BINS];
+  for (int i = threadIdx.x; i < bins; i += blockDim.x) s_hist[i] = 0u;
+  __syncthreads();
+  const float fb = (float)bins, width = __fsub_rn(hi, lo);
+  auto count = [&](float v) {
+    if (v >= lo && v <= hi) {
+      int pos = (int)__fdiv_rn(__fmul_rn(__fsub_rn(v, lo), fb), width);
+      if (pos >= bins) pos = bins - 1;
+      atomicAdd(&s_hist[pos], 1u);
+    }
+  };
+  const int64_t nvec = n / 4;
+  // chunked so that a block's 32-bit counters cannot overflow: <= 2^31 elements per block between flushes is
+  // guaranteed by the grid (>= 1 block per 2^24 elements would be enough; the grid is far larger)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    count(v.x);
+    count(v.y);
+    count(v.z);
+    count(v.w);
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = nvec * 4 + threadIdx.x; i < n; i += blockDim.x) count(x[i]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < bins; i += blockDim.x) {
+    const unsigned int c = s_hist[i];
+    if (c) atomicAdd(hist + i, (unsigned long long)c);
+  }
+}
+
+// Byte-wise table look-up y[i] = lut[x[i]]: the table lives in shared memory replicated 32 times with a 4-byte
+// interleave (entry v of copy l at word v*32 + l), so the 32 lanes of a warp always hit 32 different banks whatever
+// bytes they look up.  16 bytes per thread and iteration.
+struct LutTable {
+  uint8_t v[256];
+};
+__global__ void __launch_bounds__(256) lut_u8_kernel(const uint8_t* __restrict__ x, uint8_t* __restrict__ y, int64_t n,
+                                                     const __grid_constant__ LutTable lut) {
+  __shared__ uint32_t s_lut[256 * 32];
+  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_lut[i] = lut.v[i >> 5];
+  __syncthreads();
+  const uint32_t* tab = s_lut + (threadIdx.x & 31);
+  auto map4 = [&](uint32_t w) {
+    return tab[(w & 0xffu) << 5] | (tab[((w >> 8) & 0xffu) << 5] << 8) | (tab[((w >> 16) & 0xffu) << 5] << 16) |
+           (tab[(w >> 24) << 5] << 24);
+  };
+  const int64_t nvec = n / 16;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    v.x = map4(v.x);
+    v.y = map4(v.y);
+    v.z = map4(v.z);
+    v.w = map4(v.w);
+    reinterpret_cast<uint4*>(y)[i] = v;
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = nvec * 16 + threadIdx.x; i < n; i += blockDim.x) y[i] = lut.v[x[i]];
 }
 
 int launch_quantize_flat(const float* x, uint8_t* y, int64_t n, float inv_scale, int zp, const float* qp_dev,
@@ -327,5 +418,32 @@ extern "C" int b200q_max_pool2x2_nhwc(const uint8_t* x, uint8_t* y, int64_t b, i
 extern "C" int b200q_minmax(const float* x, int64_t n, float* out5, void* scratch, void* stream) {
   B200Q_REQUIRE(x && out5 && scratch && n > 0, "minmax: bad arguments");
   B200Q_REQUIRE((uintptr_t)x % 16 == 0, "minmax: x must be 16-byte aligned");
-  return launch_minmax(x, n, out5, scratch, (cudaStream_t)stream);
+  return launch_minmax(x, n, out5, scratch, (cudaStream_t)stream, true);
+}
+
+extern "C" int b200q_aminmax(const float* x, int64_t n, float* out2, void* scratch, void* stream) {
+  B200Q_REQUIRE(x && out2 && scratch && n > 0, "aminmax: bad arguments");
+  B200Q_REQUIRE((uintptr_t)x % 16 == 0, "aminmax: x must be 16-byte aligned");
+  return launch_minmax(x, n, out2, scratch, (cudaStream_t)stream, false);
+}
+
+extern "C" int b200q_histc(const float* x, int64_t n, float lo, float hi, int bins, int64_t* hist, void* stream) {
+  B200Q_REQUIRE((x && hist) || n == 0, "histc: null pointer");
+  B200Q_REQUIRE(bins > 0 && bins <= HISTC_MAX_BINS, "histc: bins must be in [1, %d] (got %d)", HISTC_MAX_BINS, bins);
+  B200Q_REQUIRE(lo < hi, "histc: need lo < hi (got %g, %g)", (double)lo, (double)hi);
+  B200Q_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)hist % 8 == 0, "histc: misaligned buffers");
+  if (n == 0) return 0;
+  histc_kernel<<<grid_for(n / 4 + 1, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+      x, n, lo, hi, bins, reinterpret_cast<unsigned long long*>(hist));
+  return launched("histc_kernel");
+}
+
+extern "C" int b200q_lut_u8(const uint8_t* x, uint8_t* y, int64_t n, const uint8_t* lut_host, void* stream) {
+  B200Q_REQUIRE(((x && y) || n == 0) && lut_host, "lut_u8: null pointer");
+  B200Q_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0), "lut_u8: pointers must be 16-byte aligned");
+  if (n == 0) return 0;
+  LutTable t;
+  for (int i = 0; i < 256; ++i) t.v[i] = lut_host[i];
+  lut_u8_kernel<<<grid_for(n / 16 + 1, 256, 4), 256, 0, (cudaStream_t)stream>>>(x, y, n, t);
+  return launched("lut_u8_kernel");
 }

@@ -109,6 +109,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = args.num_m_tiles * C::N_TILES;
+  pdl_launch_dependents();
 
   if (warp == TC_TMA_WARP && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -144,6 +145,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == TC_TMA_WARP) {
     // ================================================================== TMA producer
     if (lane == 0) {
+      pdl_wait();  // the A operand is the previous kernel's output
       uint32_t stage = 0, phase = 0;
       bool first_tile = true;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -373,17 +375,19 @@ static int launch_tc(const uint8_t* x, uint8_t* y, int64_t m_rows, const int8_t*
               (rq.flags & B200Q_RQ_BOUNDED) ? 1 : 0};
   const int num_tiles = num_m_tiles * C::N_TILES;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  kernel<<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(map_a, map_b, args);
-  return launched("igemm_tc_kernel");
+  return launch_kernel("igemm_tc_kernel", kernel, grid, TC_THREADS, C::SMEM_BYTES, stream, map_a, map_b, args);
 }
 
 }  // namespace b200q
 
 using namespace b200q;
 
-// B200Q_TC_STREAM_WEIGHTS=1 forces the streamed-weights variant for layers that default to resident weights
+// -DB200Q_DEV builds only: B200Q_TC_STREAM_WEIGHTS=1 forces the streamed-weights variant for layers that default to resident weights
 // (bring-up / A-B testing only).
 static bool force_streamed() {
+#ifndef B200Q_DEV
+  return false;
+#endif
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200Q_TC_STREAM_WEIGHTS");
@@ -392,8 +396,11 @@ static bool force_streamed() {
   return v == 1;
 }
 
-// B200Q_NO_HALO=1 routes the cin=64 layers through the shifted-TMA kernel as well (A-B testing only).
+// -DB200Q_DEV builds only: B200Q_NO_HALO=1 routes the cin=64 layers through the shifted-TMA kernel as well (A-B testing only).
 static bool no_halo() {
+#ifndef B200Q_DEV
+  return false;
+#endif
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200Q_NO_HALO");

@@ -1,5 +1,7 @@
 // Whole static-PTQ SimpleConvNet forward: the call order of models/baseline_model.py:58-83 on the converted
 // (int8) model, as one C-ABI call that enqueues every kernel on the caller's stream.  No allocation, no sync.
+#include <new>
+
 #include "common.cuh"
 
 using namespace b200q;
@@ -21,7 +23,7 @@ extern "C" int64_t b200q_static_workspace_bytes(int64_t b) {
 }
 
 namespace {
-// One entry per kernel the fused forward enqueues; order == launch order.  B200Q_FUSE12=1 runs conv1 and conv2 as ONE
+// One entry per kernel the fused forward enqueues; order == launch order.  In -DB200Q_DEV builds B200Q_FUSE12=1 runs conv1 and conv2 as ONE
 // kernel (conv12_fused.cu: bit-exact, but measured slower than the two kernels - 1.05 ms against 0.39 + 0.48 ms at batch
 // 16 384 - because all its requantisation work lands on eight 128-register epilogue warps).
 const char* const kStageNamesFused[] = {"conv1_conv2_pool", "conv3", "conv4_pool", "conv5",
@@ -29,8 +31,12 @@ const char* const kStageNamesFused[] = {"conv1_conv2_pool", "conv3", "conv4_pool
 const char* const kStageNamesSplit[] = {"quant_conv1", "conv2_pool", "conv3", "conv4_pool",
                                         "conv5",       "conv6_pool", "fc1",   "fc2_dequant"};
 constexpr int kMaxStages = 8;
+constexpr int kGraphKernels = 8;  // kernels one replay of a captured forward launches (b200q_launch_count bookkeeping)
 
 bool fuse12_enabled() {
+#ifndef B200Q_DEV
+  return false;  // conv12_fused.cu is not part of the product library
+#endif
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200Q_FUSE12");
@@ -69,8 +75,10 @@ int forward_impl(const b200q_static_net* net, const float* x, float* logits, int
       STEP(b200q_u8_conv3x3_first(x_u8, A, b, lut_host, &net->conv[0], stream));
       MARK();
       STEP(b200q_conv3x3_tc(A, B, b, &net->conv[1], 1, stream));
+#ifdef B200Q_DEV
     } else if (fuse12_ok(net)) {
       STEP(b200q_conv12_fused(x, B, b, net->in_inv_scale, &net->conv[0], &net->conv[1], stream));  // -> [b,16,16,64]
+#endif
     } else {
       STEP(b200q_quantize_conv3x3_first(x, A, b, net->in_inv_scale, &net->conv[0], stream));
       MARK();
@@ -134,6 +142,69 @@ extern "C" int b200q_static_forward_u8(const b200q_static_net* net, const uint8_
   return forward_impl(net, nullptr, logits, b, workspace, workspace_bytes, nullptr, nullptr, stream, x_nhwc, lut_host);
 }
 
+// ---------------------------------------------------------------------------------------------------- executor
+struct b200q_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int64_t batch = 0;
+};
+
+extern "C" int b200q_graph_create(const b200q_static_net* net, const float* x_static, float* logits_static, int64_t b,
+                                  void* workspace, int64_t workspace_bytes, int flags, void* stream, b200q_graph** out) {
+  B200Q_REQUIRE(out != nullptr, "graph_create: null out");
+  *out = nullptr;
+  B200Q_REQUIRE(net && x_static && logits_static && workspace && b > 0, "graph_create: null pointer or empty batch");
+  B200Q_REQUIRE(stream != nullptr, "graph_create: the legacy default stream cannot be captured; pass a created stream");
+  cudaStream_t s = (cudaStream_t)stream;
+  // eager first: per-device kernel attributes, lazy module loading and the tensor-map encoder are first-use work that
+  // does not belong inside a capture
+  int rc = forward_impl(net, x_static, logits_static, b, workspace, workspace_bytes, nullptr, nullptr, stream);
+  if (rc) return rc;
+  B200Q_CUDA(cudaStreamSynchronize(s));
+  B200Q_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  pdl_set((flags & B200Q_GRAPH_PDL) != 0);
+  rc = forward_impl(net, x_static, logits_static, b, workspace, workspace_bytes, nullptr, nullptr, stream);
+  pdl_set(false);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(s, &graph);  // always end the capture, also after a failed enqueue
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    (void)cudaGetLastError();
+    return rc;
+  }
+  B200Q_CUDA(e);
+  b200q_graph* g = new (std::nothrow) b200q_graph();
+  if (!g) {
+    cudaGraphDestroy(graph);
+    set_error("graph_create: out of host memory");
+    return B200Q_ERR_INVALID_ARG;
+  }
+  g->graph = graph;
+  g->batch = b;
+  if (int irc = check_cuda(cudaGraphInstantiate(&g->exec, graph, 0), "cudaGraphInstantiate")) {
+    cudaGraphDestroy(graph);
+    delete g;
+    return irc;
+  }
+  *out = g;
+  return 0;
+}
+
+extern "C" int b200q_graph_launch(b200q_graph* g, void* stream) {
+  B200Q_REQUIRE(g && g->exec, "graph_launch: null graph");
+  B200Q_CUDA(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+  note_graph_replay(g->batch == 0 ? 0 : kGraphKernels);
+  return 0;
+}
+
+extern "C" int b200q_graph_destroy(b200q_graph* g) {
+  if (!g) return 0;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+  return 0;
+}
+
 extern "C" int b200q_static_num_stages(void) { return fuse12_enabled() ? 7 : 8; }
 extern "C" const char* b200q_static_stage_name(int i) {
   const int n = b200q_static_num_stages();
@@ -148,14 +219,19 @@ extern "C" int b200q_static_forward_profiled(const b200q_static_net* net, const 
   const int kNumStages = b200q_static_num_stages();
   B200Q_REQUIRE(!fuse12_enabled() || fuse12_ok(net),
                 "static_forward_profiled: net does not qualify for the fused conv1+conv2 stage; unset B200Q_FUSE12");
-  static thread_local cudaEvent_t ev[kMaxStages + 1];
-  static thread_local int ev_device = -1;
+  // one event set per (thread, device), created on first use and kept for the life of the thread: a device change
+  // never re-creates (and so never leaks) events
+  constexpr int kMaxDevices = 64;
+  static thread_local cudaEvent_t ev_all[kMaxDevices][kMaxStages + 1];
+  static thread_local bool ev_ready[kMaxDevices] = {};
   int dev = -1;
   B200Q_CUDA(cudaGetDevice(&dev));
-  if (ev_device != dev) {  // events belong to a device: (re)create on first use per thread/device
-    for (int i = 0; i <= kMaxStages; ++i) B200Q_CUDA(cudaEventCreate(&ev[i]));
-    ev_device = dev;
+  B200Q_REQUIRE(dev >= 0 && dev < kMaxDevices, "static_forward_profiled: device index %d not supported", dev);
+  if (!ev_ready[dev]) {
+    for (int i = 0; i <= kMaxStages; ++i) B200Q_CUDA(cudaEventCreate(&ev_all[dev][i]));
+    ev_ready[dev] = true;
   }
+  cudaEvent_t* ev = ev_all[dev];
   for (int i = 0; i < kNumStages; ++i) stage_ms_host[i] = 0.f;
   if (b == 0) return 0;
   int rc = forward_impl(net, x, logits, b, workspace, workspace_bytes, nullptr, ev, stream);

@@ -31,6 +31,13 @@ int launched(const char* what) {
   return check_cuda(cudaGetLastError(), what);
 }
 
+static thread_local bool g_pdl = false;
+bool pdl_enabled() { return g_pdl; }
+void pdl_set(bool on) { g_pdl = on; }
+
+// A graph replay launches kernels that no launch site sees: the executor reports them here.
+void note_graph_replay(int kernels) { g_launches.fetch_add((uint64_t)kernels, std::memory_order_relaxed); }
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;
@@ -108,5 +115,7 @@ int encode_tensor_map(CUtensorMap* out, const void* gptr, int rank, const uint64
 }  // namespace b200q
 
 extern "C" const char* b200q_last_error(void) { return b200q::g_err; }
-extern "C" int b200q_abi_version(void) { return 3; }  // 3: + b200q_conv12_fused, b200q_u8_conv3x3_first, b200q_static_forward_u8
+// 4: b200q_linear_dynamic re-specified (tensor cores, scratch_bytes), + b200q_aminmax, b200q_histc, b200q_lut_u8,
+//    b200q_graph_*; b200q_conv12_fused and b200q_conv3x3_simt moved to the development library (-DB200Q_DEV)
+extern "C" int b200q_abi_version(void) { return 4; }
 extern "C" uint64_t b200q_launch_count(void) { return b200q::g_launches.load(std::memory_order_relaxed); }

@@ -1,12 +1,9 @@
 // CUDA-core (dp4a) kernels: the first convolution (cin=3, K=27: memory-bound, not tensor-core shaped),
-// small/dynamic linears, and a plain direct convolution used as a bring-up cross-check for the tcgen05 path.
+// small linears, and (development builds only, -DB200Q_DEV) a plain direct convolution used as a cross-check for the
+// tcgen05 path.
 #include "common.cuh"
 
 namespace b200q {
-
-int launch_minmax(const float* x, int64_t n, float* out5, void* scratch, cudaStream_t s);
-int launch_quantize_flat(const float* x, uint8_t* y, int64_t n, float inv_scale, int zp, const float* qp_dev,
-                         cudaStream_t s);
 
 __device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c) {
   int d;
@@ -102,6 +99,7 @@ __global__ void __launch_bounds__(256) conv1_kernel(const void* __restrict__ xin
   }
 }
 
+#ifdef B200Q_DEV
 // =========================================================================================================
 // Plain direct 3x3 conv, any cin % 4 == 0: one thread per (pixel, output channel).  Bring-up cross-check only.
 __global__ void conv3x3_direct_kernel(const uint8_t* __restrict__ x, uint8_t* __restrict__ y, int64_t n_img, int img,
@@ -138,23 +136,24 @@ __global__ void conv3x3_direct_kernel(const uint8_t* __restrict__ x, uint8_t* __
   }
 }
 
+#endif  // B200Q_DEV
+
 // =========================================================================================================
-// Small/dynamic linear on CUDA cores: y[b][n] = epilogue( sum_k x[b][k]*w[n][k] - zp_x*wsum[n] ).
+// Small linear on CUDA cores: y[b][n] = epilogue( sum_k x[b][k]*w[n][k] - zp_x*wsum[n] ).
 // Tile 64 (batch) x 64 (n) per 256-thread block, K stepped 64 bytes through shared memory, 4x4 outputs per thread.
-enum LinearEpilogue { EPI_REQUANT_U8 = 0, EPI_REQUANT_DEQUANT_F32 = 1, EPI_DYNAMIC_F32 = 2 };
+enum LinearEpilogue { EPI_REQUANT_U8 = 0, EPI_REQUANT_DEQUANT_F32 = 1 };
 
 struct LinearArgs {
   const uint8_t* x;
   void* y;
   const int8_t* w;
-  const int32_t* corr;   // [n] zp_x * wsum (static) or wsum (dynamic)
-  const float* mult;     // static: requant mult[n]
-  const float* bdiv;     // static: bdiv[n]; dynamic: bias[n]
-  const float* qp;       // dynamic: device {min,max,scale,inv_scale,zp}
+  const int32_t* corr;   // [n] zp_x * wsum
+  const float* mult;     // requant mult[n]
+  const float* bdiv;     // bdiv[n]
   int64_t b;
   int k, n;
   int zp_out, relu;
-  float out_scale;       // dequant scale (EPI_REQUANT_DEQUANT_F32) or w_scale (EPI_DYNAMIC_F32)
+  float out_scale;       // dequant scale (EPI_REQUANT_DEQUANT_F32)
 };
 
 template <int EPI>
@@ -194,12 +193,6 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(const LinearArgs a) {
     }
     __syncthreads();
   }
-  float s_x = 0.f;
-  int zp_dyn = 0;
-  if constexpr (EPI == EPI_DYNAMIC_F32) {
-    s_x = a.qp[2];
-    zp_dyn = (int)a.qp[4];
-  }
   const int lo = a.relu ? a.zp_out : 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -209,20 +202,12 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(const LinearArgs a) {
     for (int j = 0; j < 4; ++j) {
       const int nn = n0 + tn + j;
       if (nn >= a.n) continue;
-      if constexpr (EPI == EPI_DYNAMIC_F32) {
-        // quantized::linear_dynamic: y = f32(acc) * (s_x * s_w) + bias
-        const int t = acc[i][j] - zp_dyn * __ldg(a.corr + nn);
-        float v = __fadd_rn(__fmul_rn(__int2float_rn(t), __fmul_rn(s_x, a.out_scale)), __ldg(a.bdiv + nn));
-        if (a.relu) v = fmaxf(v, 0.0f);
-        reinterpret_cast<float*>(a.y)[bb * a.n + nn] = v;
+      const uint32_t q =
+          requant_u8(acc[i][j] - __ldg(a.corr + nn), __ldg(a.bdiv + nn), __ldg(a.mult + nn), a.zp_out, lo);
+      if constexpr (EPI == EPI_REQUANT_U8) {
+        reinterpret_cast<uint8_t*>(a.y)[bb * a.n + nn] = (uint8_t)q;
       } else {
-        const uint32_t q =
-            requant_u8(acc[i][j] - __ldg(a.corr + nn), __ldg(a.bdiv + nn), __ldg(a.mult + nn), a.zp_out, lo);
-        if constexpr (EPI == EPI_REQUANT_U8) {
-          reinterpret_cast<uint8_t*>(a.y)[bb * a.n + nn] = (uint8_t)q;
-        } else {
-          reinterpret_cast<float*>(a.y)[bb * a.n + nn] = __fmul_rn(__int2float_rn((int)q - a.zp_out), a.out_scale);
-        }
+        reinterpret_cast<float*>(a.y)[bb * a.n + nn] = __fmul_rn(__int2float_rn((int)q - a.zp_out), a.out_scale);
       }
     }
   }
@@ -236,6 +221,7 @@ template <int N>
 __global__ void __launch_bounds__(256) linear_head_dequant_kernel(const LinearArgs a) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  pdl_launch_dependents();
   uint4 w[N];
 #pragma unroll
   for (int n = 0; n < N; ++n) w[n] = __ldg(reinterpret_cast<const uint4*>(a.w + (int64_t)n * 512) + lane);
@@ -243,6 +229,7 @@ __global__ void __launch_bounds__(256) linear_head_dequant_kernel(const LinearAr
   const int corr = __ldg(a.corr + nn);
   const float bdiv = __ldg(a.bdiv + nn), mult = __ldg(a.mult + nn);
   const int lo = a.relu ? a.zp_out : 0;
+  pdl_wait();  // x is the previous kernel's output (weights and constants above are not)
   uint4 xv = make_uint4(0, 0, 0, 0);
   if (warp < a.b) xv = __ldg(reinterpret_cast<const uint4*>(a.x + (int64_t)warp * 512) + lane);
   for (int64_t img = warp; img < a.b; img += nwarps) {
@@ -301,12 +288,16 @@ static int conv_first_impl(const void* x, uint8_t* y, int64_t b, const b200q_con
                 L->img);
   B200Q_REQUIRE((uintptr_t)y % 16 == 0 && (uintptr_t)x % 4 == 0, "conv3x3_first: misaligned buffers");
   if (b == 0) return 0;
-  if (fused) {  // tensor-core version unless B200Q_NO_CONV1_TC=1 (A-B testing) or the layer lacks host mirrors
+  if (fused) {  // tensor-core version unless the layer lacks host mirrors / the BOUNDED flag (dev builds: or B200Q_NO_CONV1_TC=1)
+#ifdef B200Q_DEV
     static int no_tc = -1;
     if (no_tc < 0) {
       const char* e = getenv("B200Q_NO_CONV1_TC");
       no_tc = (e && e[0] == '1') ? 1 : 0;
     }
+#else
+    const int no_tc = 0;
+#endif
     int trc = 0;
     if (!no_tc && conv1_tc_dispatch(reinterpret_cast<const float*>(x), y, b, inv_scale, L, (cudaStream_t)stream, &trc) == 0)
       return trc;
@@ -331,6 +322,7 @@ extern "C" int b200q_quantize_conv3x3_first(const float* x, uint8_t* y, int64_t 
   return conv_first_impl(x, y, b, L, true, inv_scale, stream);
 }
 
+#ifdef B200Q_DEV
 extern "C" int b200q_conv3x3_simt(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, void* stream) {
   int rc = check_conv(x, y, b, L);
   if (rc) return rc;
@@ -343,12 +335,13 @@ extern "C" int b200q_conv3x3_simt(const uint8_t* x, uint8_t* y, int64_t b, const
       x, y, b, L->img, L->cin, L->cout, L->w, L->rq.mult, L->rq.bdiv, L->zp_x, L->rq.zp_out, L->rq.relu);
   return launched("conv3x3_direct_kernel");
 }
+#endif  // B200Q_DEV
 
 extern "C" int b200q_linear_simt(const uint8_t* x, uint8_t* y, int64_t b, const b200q_linear* L, void* stream) {
   int rc = check_linear(x, y, b, L);
   if (rc) return rc;
   if (b == 0) return 0;
-  LinearArgs a{x, y, L->w, L->corr, L->rq.mult, L->rq.bdiv, nullptr, b, L->k, L->n, L->rq.zp_out, L->rq.relu, 0.f};
+  LinearArgs a{x, y, L->w, L->corr, L->rq.mult, L->rq.bdiv, b, L->k, L->n, L->rq.zp_out, L->rq.relu, 0.f};
   return launch_linear<EPI_REQUANT_U8>(a, (cudaStream_t)stream);
 }
 
@@ -357,30 +350,12 @@ extern "C" int b200q_linear_dequant(const uint8_t* x, float* y, int64_t b, const
   int rc = check_linear(x, y, b, L);
   if (rc) return rc;
   if (b == 0) return 0;
-  LinearArgs a{x, y, L->w, L->corr, L->rq.mult, L->rq.bdiv, nullptr, b, L->k, L->n, L->rq.zp_out, L->rq.relu,
+  LinearArgs a{x, y, L->w, L->corr, L->rq.mult, L->rq.bdiv, b, L->k, L->n, L->rq.zp_out, L->rq.relu,
                out_scale};
   if (L->k == 512 && L->n == 10 && (uintptr_t)x % 16 == 0 && (uintptr_t)L->w % 16 == 0) {
     const int64_t warps = b < (int64_t)num_sms() * 64 ? b : (int64_t)num_sms() * 64;  // <= 8 blocks of 8 warps per SM
-    linear_head_dequant_kernel<10><<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(a);
-    return launched("linear_head_dequant_kernel");
+    return launch_kernel("linear_head_dequant_kernel", linear_head_dequant_kernel<10>, (int)((warps + 7) / 8), 256, 0,
+                         (cudaStream_t)stream, a);
   }
   return launch_linear<EPI_REQUANT_DEQUANT_F32>(a, (cudaStream_t)stream);
-}
-
-extern "C" int b200q_linear_dynamic(const float* x, float* y, int64_t b, int k, int n, const int8_t* w,
-                                    const int32_t* wsum, float w_scale, const float* bias, int relu, uint8_t* xq,
-                                    void* scratch, void* stream) {
-  B200Q_REQUIRE(x && y && w && wsum && bias && xq && scratch, "linear_dynamic: null pointer");
-  B200Q_REQUIRE(b > 0 && k > 0 && k % 4 == 0 && n > 0, "linear_dynamic: bad shape b=%lld k=%d n=%d", (long long)b, k, n);
-  B200Q_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)xq % 16 == 0 && (uintptr_t)w % 4 == 0,
-                "linear_dynamic: misaligned buffers");
-  cudaStream_t s = (cudaStream_t)stream;
-  // scratch: [0, 8208) min/max partials + counter; qparams {min,max,scale,inv_scale,zp} right after (16B aligned)
-  float* qp = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 8224);
-  int rc = launch_minmax(x, b * k, qp, scratch, s);
-  if (rc) return rc;
-  rc = launch_quantize_flat(x, xq, b * k, 0.f, 0, qp, s);
-  if (rc) return rc;
-  LinearArgs a{xq, y, w, wsum, nullptr, bias, qp, b, k, n, 0, relu, w_scale};
-  return launch_linear<EPI_DYNAMIC_F32>(a, s);
 }

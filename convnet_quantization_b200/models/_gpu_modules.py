@@ -5,7 +5,11 @@ calls ``eval()/cpu()/model(cpu_images)`` and ``outputs.topk`` on the result):
 * ``forward`` accepts fp32 NCHW ``[B,3,32,32]`` on CPU **or** CUDA and returns fp32 logits ``[B,10]`` on the input's
   device (H2D / D2H done here when the caller hands CPU tensors);
 * ``.cpu()`` / ``.to('cpu')`` never tear the GPU engine down (the arithmetic has no CPU fallback);
-* ``.to('cuda:N')`` re-homes the engine; everything mutates in place because the driver discards ``.to()``'s result.
+* ``.to('cuda:N')`` re-homes the engine; everything mutates in place because the driver discards ``.to()``'s result;
+* ``forward`` on a CUDA input synchronises the stream before returning (``sync_on_forward``, default on): the
+  reference's benchmark reads ``time.time()`` right after ``model(data)`` without a device synchronize
+  (``utils/inference_benchmark.py:93-100``), so an asynchronous return would make it time the launch, not the work.
+  Pipelines that manage their own streams call ``engine.forward`` (never synchronises) or clear the flag.
 """
 from __future__ import annotations
 
@@ -29,9 +33,12 @@ class _GpuResident(nn.Module):
     """Common device handling: the engine lives on ``self.engine_device`` regardless of ``.cpu()``."""
 
     quantized = True  # sniffed by utils/model_evaluator.py:25,66
+    sync_on_forward = True
 
     def __init__(self, device=None):
         super().__init__()
+        if isinstance(device, int):
+            device = torch.device("cuda", device)
         self.engine_device = torch.device(device) if device is not None else _default_device()
         if self.engine_device.type != "cuda":
             raise _lib.B200QError("engine device must be CUDA")
@@ -43,7 +50,11 @@ class _GpuResident(nn.Module):
 
     def to(self, *args, **kwargs):
         device = kwargs.get("device", args[0] if args else None)
-        if isinstance(device, str):
+        if isinstance(device, bool):
+            device = None
+        elif isinstance(device, int):  # model.to(1) == model.to("cuda:1"), as torch.nn.Module.to reads it
+            device = torch.device("cuda", device)
+        elif isinstance(device, str):
             device = torch.device(device)
         if isinstance(device, torch.device) and device.type == "cuda":
             if device.index is None:
@@ -62,9 +73,12 @@ class _GpuResident(nn.Module):
         if x.dtype != torch.float32:
             x = x.float()
         if x.is_cuda and x.device == self.engine_device:
-            return fn(x.contiguous())
+            y = fn(x.contiguous())
+            if self.sync_on_forward:
+                torch.cuda.current_stream(self.engine_device).synchronize()
+            return y
         y = fn(x.to(self.engine_device, non_blocking=True).contiguous())
-        return y.to(x.device)
+        return y.to(x.device)  # device -> host (or peer) copy: synchronises by itself
 
 
 class B200StaticQuantizedNet(_GpuResident):
@@ -167,7 +181,10 @@ class B200StaticQuantizedNet(_GpuResident):
             return self._forward_host(pixels, u8=True)
         if not pixels.is_cuda:
             return torch.empty((0, 10), dtype=torch.float32)
-        return self.engine.forward_u8(pixels)
+        y = self.engine.forward_u8(pixels)
+        if self.sync_on_forward:
+            torch.cuda.current_stream(self.engine_device).synchronize()
+        return y
 
     @torch.no_grad()
     def forward_with_taps(self, x):
@@ -228,6 +245,8 @@ class B200DynamicQuantizedNet(_GpuResident):
         return x.reshape(x.shape[0], -1).contiguous()
 
     def _forward_dev(self, x):
+        if x.shape[0] == 0:
+            return torch.empty((0, 10), dtype=torch.float32, device=x.device)
         x = self.features(x)
         if self.bn is None:
             x = ops.linear_dynamic(x, self.fc["fc1"], relu=True)
@@ -243,4 +262,88 @@ class B200DynamicQuantizedNet(_GpuResident):
         sd = {k: v for k, v in self._fused_cpu.state_dict().items() if not k.startswith(("fc1", "fc2"))}
         for n, (w, s, b) in self._fc_cpu.items():
             sd[f"{n}.weight"], sd[f"{n}.scale"], sd[f"{n}.bias"] = w, torch.tensor(s), b
+        return sd
+
+
+class B200SandwichQuantizedNet(_GpuResident):
+    """The custom variant *as intended* (``models/custom_quantization_model.py:34-58, 202-261``):
+    each conv and ``fc1`` is QuantStub -> int8 layer -> DeQuantStub, ReLU / max-pool run in fp32 between the
+    sandwiches, ``fc2`` is fp32.  On the GPU the fp32 detours collapse without changing a bit:
+
+    * the int8 layers are the tensor-core kernels of the static net with ReLU fusion OFF (the sandwich's conv output
+      observer sees pre-ReLU values) and the 2x2 max-pool still fused into conv2/4/6;
+    * DeQuantStub -> fp32 ReLU (-> fp32 max-pool) -> next QuantStub is a monotone uint8 -> uint8 map, applied as a
+      256-entry table (``b200q_lut_u8``) that ``ptq.sandwich_boundary_lut`` evaluates with the reference's own torch
+      ops; being monotone it commutes with the max-pool, so it runs on the pooled (4x smaller) tensor;
+    * ``fc1``'s uint8 output is ReLU'd and dequantised (``b200q_relu_q`` + ``b200q_dequantize`` == fp32 ReLU of the
+      dequantised tensor), then ``fc2`` is an fp32 ATen GEMM (the tolerance part of this variant)."""
+
+    is_custom_quantized = True
+
+    def __init__(self, sparams: dict, device=None):
+        super().__init__(device)
+        self.sparams = sparams
+        self._build(self.engine_device)
+
+    def _build(self, device):
+        from .. import ptq
+        from ..packing import PackedConv, PackedLinear
+        sp = self.sparams
+        names = ptq.SANDWICH_LAYERS
+        with torch.cuda.device(device):
+            self.convs = [PackedConv(n, sp[n], sp[n]["in_scale"], sp[n]["in_zp"], device, relu=False) for n in names[:6]]
+            self.fc1 = PackedLinear("fc1", sp["fc1"], sp["fc1"]["in_scale"], sp["fc1"]["in_zp"], device, relu=False,
+                                    nhwc_from=(256, 4, 4))
+            self.fc2_w = sp["fc2"]["weight"].to(device)
+            self.fc2_b = sp["fc2"]["bias"].to(device)
+        # boundary tables: output qparams of layer i -> input qparams of layer i+1 (host uint8 [256])
+        self.luts = [ptq.sandwich_boundary_lut(sp[a]["out_scale"], sp[a]["out_zp"], sp[b]["in_scale"], sp[b]["in_zp"])
+                     for a, b in zip(names[:-1], names[1:])]
+
+    def _rehome(self, device):
+        self._build(device)
+        self.engine_device = device
+
+    @torch.no_grad()
+    def _forward_dev(self, x, taps: dict | None = None):
+        sp = self.sparams
+        a = ops.quantize_conv2d_first(x, sp["conv1"]["in_scale"], self.convs[0])
+        if taps is not None:
+            taps["conv1"] = a
+        for i in range(1, 6):
+            a = ops.lut_u8(a, self.luts[i - 1])
+            a = ops.conv2d_q(a, self.convs[i], pool2x2=(i % 2 == 1) and taps is None)
+            if taps is not None:
+                taps[f"conv{i + 1}"] = a
+                if i % 2 == 1:
+                    a = ops.max_pool2d_q(a)
+        a = ops.lut_u8(a, self.luts[5]).reshape(a.shape[0], -1)  # NHWC [B,4,4,256]; fc1's columns are permuted to match
+        h = ops.linear_q(a, self.fc1)
+        if taps is not None:
+            taps["fc1"] = h
+        h = ops.dequantize(ops.relu_q(h, sp["fc1"]["out_zp"]), sp["fc1"]["out_scale"], sp["fc1"]["out_zp"])
+        return torch.addmm(self.fc2_b, h, self.fc2_w.t())
+
+    @torch.no_grad()
+    def forward(self, x):
+        if x.shape[0] == 0:
+            return torch.empty((0, 10), dtype=torch.float32, device=x.device)
+        return self._run(x, self._forward_dev)
+
+    @torch.no_grad()
+    def forward_with_taps(self, x):
+        """(logits, {layer: uint8 NHWC output of the sandwich's int8 layer, before ReLU}) - parity-test hook."""
+        taps: dict = {}
+        logits = self._forward_dev(x.to(self.engine_device).float().contiguous(), taps)
+        return logits, taps
+
+    def state_dict(self, *args, **kwargs):
+        sd = {}
+        for name, L in self.sparams.items():
+            if name == "fc2":
+                sd["fc2.weight"], sd["fc2.bias"] = L["weight"], L["bias"]
+                continue
+            sd[f"{name}.quant.scale"], sd[f"{name}.quant.zero_point"] = torch.tensor(L["in_scale"]), torch.tensor(L["in_zp"])
+            sd[f"{name}.weight"], sd[f"{name}.weight_scales"], sd[f"{name}.bias"] = L["w_int8"], L["w_scales"].float(), L["bias"]
+            sd[f"{name}.scale"], sd[f"{name}.zero_point"] = torch.tensor(L["out_scale"]), torch.tensor(L["out_zp"])
         return sd

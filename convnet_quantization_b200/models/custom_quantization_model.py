@@ -4,15 +4,19 @@ the ResNet50 wrappers in that file are out of scope).
 As written, the reference wraps every layer in ``QuantStub``/``DeQuantStub`` but never calls ``prepare``/``convert``,
 so the stubs are identity and the model is the BN-folded **fp32** net.  ``mode="as_written"`` (default)
 reproduces exactly that (fp32 ATen ops on whatever device the driver moves the module to — the tolerance path);
-``mode="int8"`` is the evident intent retargeted to the engine: per-channel int8 weights with fused ReLU, i.e. the
-static-PTQ CUDA path.
+``mode="sandwich"`` is the wrapper *as intended*: ``prepare``/``convert`` really applied to the per-layer
+QuantStub -> int8 layer -> DeQuantStub sandwiches (with the two repairs without which the converted reference class
+crashes), ReLU / pool in fp32, ``fc2`` fp32 - executed on the GPU by ``B200SandwichQuantizedNet`` and
+bit-exact, layer by layer, against that converted torch model;
+``mode="int8"`` is the fully fused reading (per-channel int8 weights with fused ReLU, activations stay int8 between
+layers), i.e. the static-PTQ CUDA path.
 """
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ptq, synth
-from ._gpu_modules import B200StaticQuantizedNet
+from ._gpu_modules import B200SandwichQuantizedNet, B200StaticQuantizedNet
 from .baseline_model import CONV_PLAN, FC_IN, SimpleConvNet
 
 
@@ -71,7 +75,7 @@ class CustomQuantizedSimpleConvNet(nn.Module):
 class CustomQuantizationModel(nn.Module):
     def __init__(self, mode: str = "as_written", device=None):
         super().__init__()
-        if mode not in ("as_written", "int8"):
+        if mode not in ("as_written", "sandwich", "int8"):
             raise ValueError(f"unknown mode {mode!r}")
         self.mode = mode
         self.device = device
@@ -86,10 +90,13 @@ class CustomQuantizationModel(nn.Module):
     def quantize(self, calibration_data_loader=None):
         self.model.eval()
         self.model = self.model.cpu()
-        if self.mode == "int8":
+        if self.mode in ("int8", "sandwich"):
             batches = synth.calibration_batches() if calibration_data_loader is None else (
                 (b[0] if isinstance(b, (tuple, list)) else b) for b in calibration_data_loader)
-            self.quantized_model = B200StaticQuantizedNet(ptq.calibrate_static(self.model, batches), self.device)
+            if self.mode == "int8":
+                self.quantized_model = B200StaticQuantizedNet(ptq.calibrate_static(self.model, batches), self.device)
+            else:
+                self.quantized_model = B200SandwichQuantizedNet(ptq.calibrate_sandwich(self.model, batches), self.device)
             self.quantized_model.is_custom_quantized = True
         else:
             self.model = ptq.fuse_bn(self.model)

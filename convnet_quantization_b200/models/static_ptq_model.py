@@ -41,19 +41,21 @@ class StaticPTQModel:
         self.quantized_model = None
         self.qparams = None
 
-    def quantize(self, calibration_data_loader=None):
+    def quantize(self, calibration_data_loader=None, calibration_device=None):
+        """``calibration_device="cuda"``: run the calibration forward and the observers' reductions on the GPU
+        (``ptq.B200HistogramObserver``).  Default: the host, one thread (reproducible scales)."""
         self.fp32_model.eval()
         if self.mode == "as_written":
             from .dynamic_ptq_model import dynamic_linear_weights
             net = self.fp32_model.cpu()
             # convolutions: BN folded for execution only (numerically the unfused eval-mode net); fc1 is quantised from
             # the UNFUSED weights as the reference does, so its batch-norm runs after the dynamic linear
-            self.quantized_model = B200DynamicQuantizedNet(ptq.fold_identity(net), dynamic_linear_weights(net, fused=False),
+            self.quantized_model = B200DynamicQuantizedNet(ptq.fuse_bn(net), dynamic_linear_weights(net, fused=False),
                                                            self.device, bn_after_fc1=net.bn7)
             return self.quantized_model
         batches = (synth.calibration_batches() if calibration_data_loader is None
                    else _calibration_tensors(calibration_data_loader))
-        self.qparams = ptq.calibrate_static(self.fp32_model, batches)
+        self.qparams = ptq.calibrate_static(self.fp32_model, batches, device=calibration_device)
         self.quantized_model = B200StaticQuantizedNet(self.qparams, self.device)
         return self.quantized_model
 

@@ -6,7 +6,12 @@ quantisation are done with the same ``torch.ao.quantization`` eager-mode calls t
 ``QuantStub``/``DeQuantStub``/``prepare``/``convert``/``get_default_qconfig`` imported at
 ``models/custom_quantization_model.py:5``), so the resulting integers are identical to what a torch CPU
 model would hold.  The converted torch module is thrown away; only its integers/scales are kept and
-packed for the CUDA engine (``packing.py``).  GPU-side calibration is SURVEY.md §8(f) rank 2 ("next").
+packed for the CUDA engine (``packing.py``).
+
+GPU-side calibration: with ``device="cuda"`` the fp32 net runs on the GPU and the
+activation observers reduce every observed tensor there (``B200HistogramObserver``: ``b200q_aminmax`` +
+``b200q_histc``); only 8 + 16 384 bytes per observation cross PCIe, and the O(bins) bookkeeping that turns histograms
+into (scale, zero_point) stays torch's own ``HistogramObserver`` code on the host.
 """
 from __future__ import annotations
 
@@ -39,12 +44,6 @@ def fuse_bn(fp32_net: nn.Module) -> nn.Module:
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         return torch.ao.quantization.fuse_modules(net, FUSE_LIST, inplace=False)
-
-
-def fold_identity(fp32_net: nn.Module) -> nn.Module:
-    """BN folded into the preceding conv/linear for *execution* only (numerically the unfused eval-mode net up to
-    fp32 rounding); used by ``StaticPTQModel(mode="as_written")`` whose reference code does not fuse."""
-    return fuse_bn(fp32_net)
 
 
 class _CalibWrap(nn.Module):
@@ -80,18 +79,92 @@ class single_thread:
         torch.set_num_threads(self.n)
 
 
-def calibrate_static(fp32_net: nn.Module, calib_batches) -> dict:
+class B200HistogramObserver(torch.ao.quantization.HistogramObserver):
+    """``HistogramObserver`` whose per-tensor reductions run on the GPU.
+
+    For a CUDA input the two O(numel) steps of ``HistogramObserver.forward`` - ``torch.aminmax(x)`` and
+    ``torch.histc(x, bins, min, max)`` - are ``ops.aminmax`` / ``ops.histc`` (hand-written kernels with ATen's CPU
+    binning rule, so the counts equal what the CPU observer would have counted for the same tensor).  The observer's
+    state (2048-bin histogram, running min/max) stays on the HOST whatever ``.to()`` / ``.cuda()`` is applied to the
+    model around it, and everything downstream (``_combine_histograms``, ``_non_linear_param_search``,
+    ``calculate_qparams``) is the parent class unchanged."""
+
+    def _apply(self, fn, recurse=True):  # state stays on the host: model.cuda() must not move it
+        return self
+
+    def _histc(self, x, lo, hi):
+        from . import ops
+        return ops.histc(x, self.bins, float(lo), float(hi)).cpu().to(self.histogram.dtype)
+
+    def forward(self, x_orig: torch.Tensor) -> torch.Tensor:
+        if not x_orig.is_cuda:
+            return super().forward(x_orig)
+        if x_orig.numel() == 0:
+            return x_orig
+        from . import ops
+        x = x_orig.detach().float().contiguous()
+        mm = ops.aminmax(x).cpu()
+        x_min, x_max = mm[0], mm[1]
+        if not bool(torch.isfinite(mm).all()):
+            raise ValueError("B200HistogramObserver: non-finite values in the observed tensor")
+        if self.min_val == float("inf") or self.max_val == float("-inf"):  # first observation
+            self.min_val.resize_(x_min.shape).copy_(x_min)
+            self.max_val.resize_(x_max.shape).copy_(x_max)
+            hist = self._histc(x, x_min, x_max)
+            self.histogram.detach_().resize_(hist.shape)
+            self.histogram.copy_(hist)
+            return x_orig
+        new_min, new_max = torch.min(self.min_val, x_min), torch.max(self.max_val, x_max)
+        update = self._histc(x, new_min, new_max)
+        if new_min == self.min_val and new_max == self.max_val:
+            combined = self.histogram + update
+        else:
+            combined = self._combine_histograms(self.histogram, self.min_val, self.max_val, update, new_min, new_max)
+            self.min_val.detach_().resize_(new_min.shape)
+            self.min_val.copy_(new_min)
+            self.max_val.detach_().resize_(new_max.shape)
+            self.max_val.copy_(new_max)
+        self.histogram.detach_().resize_(combined.shape)
+        self.histogram.copy_(combined)
+        return x_orig
+
+
+def fbgemm_qconfig(device=None):
+    """``get_default_qconfig('fbgemm')``; for a CUDA ``device`` the same configuration with the activation observer
+    replaced by :class:`B200HistogramObserver`."""
+    base = torch.ao.quantization.get_default_qconfig("fbgemm")
+    if device is None or torch.device(device).type != "cuda":
+        return base
+    return torch.ao.quantization.QConfig(activation=B200HistogramObserver.with_args(reduce_range=True), weight=base.weight)
+
+
+def _run_calibration(prepared: nn.Module, calib_batches, device=None) -> nn.Module:
+    """Feed the calibration batches through a prepared model: on the host (one thread: the observed ranges must not
+    depend on the fp32 summation order of a thread count) or, with a CUDA ``device``, on the GPU."""
+    with torch.no_grad():
+        if device is None or torch.device(device).type != "cuda":
+            with single_thread():
+                for xb in calib_batches:
+                    prepared(xb.detach().cpu().float())
+            return prepared
+        prepared = prepared.to(device)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            for xb in calib_batches:
+                prepared(xb.detach().to(device, non_blocking=True).float())
+        return prepared.cpu()
+
+
+def calibrate_static(fp32_net: nn.Module, calib_batches, device=None) -> dict:
     """Returns the static-PTQ parameter dict:
-    ``{"in_scale", "in_zp", layer: {"w_int8", "w_scales"(f64), "bias"(f32), "out_scale", "out_zp"}}``."""
+    ``{"in_scale", "in_zp", layer: {"w_int8", "w_scales"(f64), "bias"(f32), "out_scale", "out_zp"}}``.
+    ``device="cuda"`` calibrates on the GPU (module docstring); default: host."""
     select_engine()
-    with warnings.catch_warnings(), single_thread():
+    with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         wrap = _CalibWrap(fuse_bn(fp32_net)).eval()
-        wrap.qconfig = torch.ao.quantization.get_default_qconfig("fbgemm")
+        wrap.qconfig = fbgemm_qconfig(device)
         prepared = torch.ao.quantization.prepare(wrap, inplace=False)
-        with torch.no_grad():
-            for xb in calib_batches:
-                prepared(xb.detach().cpu().float())
+        prepared = _run_calibration(prepared, calib_batches, device)
         q = torch.ao.quantization.convert(prepared, inplace=False)
     out = {"in_scale": float(q.quant.scale), "in_zp": int(q.quant.zero_point)}
     for name in QUANT_LAYERS:
@@ -103,3 +176,54 @@ def calibrate_static(fp32_net: nn.Module, calib_batches) -> dict:
                      "bias": mod.bias().detach().clone().float(), "out_scale": float(mod.scale),
                      "out_zp": int(mod.zero_point)}
     return out
+
+
+# ------------------------------------------------------------------ the per-layer "sandwich" variant
+SANDWICH_LAYERS = ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "fc1")
+
+
+def calibrate_sandwich(fp32_net: nn.Module, calib_batches, device=None) -> dict:
+    """The custom variant *as intended* by ``models/custom_quantization_model.py:34-58, 202-261``: every conv and
+    ``fc1`` in its own QuantStub -> int8 layer -> DeQuantStub sandwich, ReLU / max-pool in fp32 between them, ``fc2``
+    fp32.  The reference never calls ``prepare``/``convert`` on it (and crashes if one does: the outer stubs double-
+    quantise), so this is the reference's wrapper class with the two repairs of survey probe P3: the OUTER
+    ``quant``/``dequant`` stubs and ``fc2`` get no qconfig, and the flatten is a ``reshape``.
+
+    Returns ``{layer: {"in_scale", "in_zp", "w_int8", "w_scales", "bias", "out_scale", "out_zp"}, "fc2": {"weight",
+    "bias"}}`` for ``layer`` in ``SANDWICH_LAYERS``."""
+    from .models.custom_quantization_model import CustomQuantizedSimpleConvNet
+    select_engine()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = CustomQuantizedSimpleConvNet(fuse_bn(fp32_net)).eval()
+        net.qconfig = fbgemm_qconfig(device)
+        net.quant.qconfig = None
+        net.dequant.qconfig = None
+        net.fc2.qconfig = None
+        prepared = torch.ao.quantization.prepare(net, inplace=False)
+        prepared = _run_calibration(prepared, calib_batches, device)
+        q = torch.ao.quantization.convert(prepared, inplace=False)
+    out = {}
+    for name in SANDWICH_LAYERS:
+        sw = getattr(q, name)
+        mod = sw.conv if hasattr(sw, "conv") else sw.linear
+        w = mod.weight()
+        if int(w.q_per_channel_zero_points().abs().max()) != 0:
+            raise RuntimeError(f"{name}: expected symmetric per-channel weights")
+        out[name] = {"in_scale": float(sw.quant.scale), "in_zp": int(sw.quant.zero_point),
+                     "w_int8": w.int_repr().clone(), "w_scales": w.q_per_channel_scales().clone(),
+                     "bias": mod.bias().detach().clone().float(), "out_scale": float(mod.scale),
+                     "out_zp": int(mod.zero_point)}
+    out["fc2"] = {"weight": q.fc2.weight.detach().clone().float(), "bias": q.fc2.bias.detach().clone().float()}
+    return out
+
+
+def sandwich_boundary_lut(out_scale: float, out_zp: int, next_scale: float, next_zp: int) -> torch.Tensor:
+    """uint8 ``[256]``: what DeQuantStub -> ``F.relu`` (fp32) -> the next sandwich's QuantStub make of a quantized
+    value, evaluated for all 256 values with those very torch CPU ops.  The map is monotone non-decreasing, so it
+    commutes with the fp32 max-pool that may sit between the ReLU and the next QuantStub."""
+    q = torch._make_per_tensor_quantized_tensor(torch.arange(256, dtype=torch.uint8), float(out_scale), int(out_zp))
+    v = F.relu(q.dequantize())
+    lut = torch.quantize_per_tensor(v, float(next_scale), int(next_zp), torch.quint8).int_repr().contiguous()
+    assert bool((lut[1:] >= lut[:-1]).all())
+    return lut

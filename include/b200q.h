@@ -99,8 +99,27 @@ int b200q_dequantize(const uint8_t* q, float* y, int64_t n, float scale, int zp,
 int b200q_relu_q(const uint8_t* q, uint8_t* y, int64_t n, int zp, void* stream);
 /* aten::quantized_max_pool2d k=2 s=2 on uint8 NHWC [b,h,w,c] -> [b,h/2,w/2,c]; c % 16 == 0. */
 int b200q_max_pool2x2_nhwc(const uint8_t* x, uint8_t* y, int64_t b, int h, int w, int c, void* stream);
-/* min/max over n fp32 values -> out[0]=min(x,0), out[1]=max(x,0); scratch >= 2*1024 floats + 1 uint32 counter (zeroed). */
-int b200q_minmax(const float* x, int64_t n, float* out2, void* scratch, void* stream);
+/* Bytes of device scratch (zero-initialised ONCE by the caller, self-resetting afterwards) that b200q_minmax,
+ * b200q_aminmax and b200q_linear_dynamic need: block partials, the last-block counter and the 8-float qparams block. */
+#define B200Q_REDUCE_SCRATCH_BYTES 8256
+/* Dynamic range for quantized::linear_dynamic: out5 = {min(x,0), max(x,0), scale, 1/scale, zero_point} with the
+ * (scale, zero_point) of ChooseQuantizationParams(min, max, 0, 255, reduce_range=true)
+ * (ATen/native/quantized/cpu/QuantUtils.h), computed on device.  scratch: B200Q_REDUCE_SCRATCH_BYTES. */
+int b200q_minmax(const float* x, int64_t n, float* out5, void* scratch, void* stream);
+/* torch.aminmax as the calibration observers call it (torch/ao/quantization/observer.py: MinMaxObserver /
+ * HistogramObserver.forward, reached from prepare() at models/custom_quantization_model.py:5): out2 = {min(x), max(x)}
+ * (no zero extension).  scratch: B200Q_REDUCE_SCRATCH_BYTES. */
+int b200q_aminmax(const float* x, int64_t n, float* out2, void* scratch, void* stream);
+/* torch.histc(x, bins, min=lo, max=hi) for the HistogramObserver (GPU-side calibration):
+ * hist[i] += |{x : bin(x) == i}| with ATen's CPU rule bin(x) = int(((x - lo) * bins) / (hi - lo)) evaluated in fp32
+ * (bin == bins -> bins - 1; values outside [lo, hi] are ignored; lo < hi required - the caller widens a degenerate
+ * range to [lo-1, hi+1] like ATen does).  hist: int64[bins] on the device, ACCUMULATED into (zero it first).
+ * bins <= 4096. */
+int b200q_histc(const float* x, int64_t n, float lo, float hi, int bins, int64_t* hist, void* stream);
+/* y[i] = lut[x[i]]: byte-wise table look-up (lut_host: HOST uint8[256]).  Used by the per-layer "sandwich" variant
+ * (models/custom_quantization_model.py:34-58): DeQuantStub -> fp32 ReLU -> QuantStub of the next layer is a monotone
+ * uint8 -> uint8 map, evaluated once per value of the table with the reference's own ops. */
+int b200q_lut_u8(const uint8_t* x, uint8_t* y, int64_t n, const uint8_t* lut_host, void* stream);
 
 /* ---- convolutions ---------------------------------------------------------------------------- */
 
@@ -116,6 +135,7 @@ int b200q_quantize_conv3x3_first(const float* x, uint8_t* y, int64_t b, float in
  * route.  L must be conv1 (cin 4, cout 64, img 32) with host mirrors and B200Q_RQ_BOUNDED. */
 int b200q_u8_conv3x3_first(const uint8_t* x_nhwc, uint8_t* y, int64_t b, const uint8_t* lut_host,
                            const b200q_conv3x3* L, void* stream);
+#ifdef B200Q_DEV  /* development library (libb200q_dev.so) only: measured slower than the two kernels it replaces */
 /* The first two layers and the first max-pool in one kernel (conv1's output never leaves shared memory):
  * aten::quantize_per_tensor + quantized::conv2d + relu (L1: cin 4, cout 64, img 32) + quantized::conv2d + relu
  * (L2: cin 64, cout 64) + aten::quantized_max_pool2d: fp32 NCHW [b,3,32,32] -> uint8 NHWC [b,16,16,64].
@@ -123,11 +143,14 @@ int b200q_u8_conv3x3_first(const uint8_t* x_nhwc, uint8_t* y, int64_t b, const u
  * their constants and L1 must be B200Q_RQ_BOUNDED; otherwise B200Q_ERR_INVALID_ARG (use the separate entry points). */
 int b200q_conv12_fused(const float* x, uint8_t* y, int64_t b, float inv_scale, const b200q_conv3x3* L1,
                        const b200q_conv3x3* L2, void* stream);
+#endif
 /* tcgen05 implicit-GEMM 3x3 conv (cin % 64 == 0): uint8 NHWC [b,img,img,cin] -> uint8 NHWC [b,img,img,cout]
  * or, with pool2x2 != 0, the 2x2/2 max-pooled [b,img/2,img/2,cout] (aten::quantized_max_pool2d fused). */
 int b200q_conv3x3_tc(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, int pool2x2, void* stream);
+#ifdef B200Q_DEV  /* development library only */
 /* Reference-grade CUDA-core version of the same op (bring-up cross-check; not used by the net). */
 int b200q_conv3x3_simt(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, void* stream);
+#endif
 
 /* ---- linear ----------------------------------------------------------------------------------- */
 
@@ -138,12 +161,18 @@ int b200q_linear_simt(const uint8_t* x, uint8_t* y, int64_t b, const b200q_linea
 /* Small linear fused with aten::dequantize (fc2 + DeQuantStub): uint8 [b,k] -> fp32 [b,n]. */
 int b200q_linear_dequant(const uint8_t* x, float* y, int64_t b, const b200q_linear* L, float out_scale, void* stream);
 
-/* quantized::linear_dynamic(x, W, reduce_range=True) (models/dynamic_ptq_model.py:302-306 -> nnqd.Linear):
- * per-tensor min/max of x on device -> (scale, zp) on device -> quantize -> int8 GEMM -> y = f32(acc)*(s_x*s_w)+bias.
- * x fp32 [b,k]; w int8 [n][k] per-tensor symmetric scale w_scale; wsum[n] = sum_k w; bias fp32 [n]; y fp32 [b,n].
- * xq: scratch uint8 [b*k]; scratch: >= 2*1024 floats + 16 bytes, zero-initialised once. */
+/* quantized::linear_dynamic(x, W, reduce_range=True) (models/dynamic_ptq_model.py:302-306 -> nnqd.Linear), two launches:
+ * (1) per-tensor min/max of the WHOLE input -> (scale, zp) on device (b200q_minmax); (2) one tcgen05 GEMM kernel whose
+ * producer warps quantise the fp32 rows straight into the swizzled K-major shared-memory tiles the tensor core reads
+ * (the uint8 activations never exist in HBM), weights by TMA, epilogue y = f32(acc - zp*wsum[n]) * (s_x*s_w) + bias[n]
+ * (+ ReLU when relu != 0, the F.relu that follows fc1 at models/baseline_model.py:80).
+ * x fp32 [b,k] (k % 64 == 0); w int8 [n][k], per-tensor symmetric scale w_scale, n == 512 or n <= 16;
+ * wsum[n] = sum_k w; bias fp32 [n]; y fp32 [b,n].  scratch: B200Q_REDUCE_SCRATCH_BYTES (its qparams block is left
+ * holding {min, max, scale, 1/scale, zp} of this call at byte offset B200Q_REDUCE_QPARAMS_OFFSET). */
+#define B200Q_REDUCE_QPARAMS_OFFSET 8224
 int b200q_linear_dynamic(const float* x, float* y, int64_t b, int k, int n, const int8_t* w, const int32_t* wsum,
-                         float w_scale, const float* bias, int relu, uint8_t* xq, void* scratch, void* stream);
+                         float w_scale, const float* bias, int relu, void* scratch, int64_t scratch_bytes,
+                         void* stream);
 
 /* ---- whole static-PTQ network ------------------------------------------------------------------ */
 
@@ -165,6 +194,23 @@ int b200q_static_forward(const b200q_static_net* net, const float* x, float* log
 /* Same forward from raw uint8 NHWC pixels [b,32,32,3] (see b200q_u8_conv3x3_first for lut_host). */
 int b200q_static_forward_u8(const b200q_static_net* net, const uint8_t* x_nhwc, const uint8_t* lut_host, float* logits,
                             int64_t b, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- whole-network executor -----------------------------------------------------------------
+ * The forward captured ONCE as a CUDA graph for a fixed batch and fixed buffers, with programmatic dependent launch
+ * between the layer kernels (kernel N+1's prologue - weights into shared memory, TMEM allocation, pad initialisation -
+ * overlaps kernel N), replayed with one call.  Serves the operating points of the reference's own driver
+ * (utils/inference_benchmark.py:126-138: batch 1 and batch 32), where eight separate launches are latency-bound.
+ * x_static / logits_static / workspace are caller-owned device buffers that must stay valid (and must not be
+ * written by anyone else while a replay is in flight); the caller copies its input into x_static before each launch.
+ * All three calls take the stream the graph is captured / replayed on.  The handle is not thread-safe. */
+typedef struct b200q_graph b200q_graph;
+#define B200Q_GRAPH_PDL 1   /* flags: programmatic dependent launch between the layer kernels */
+/* Runs one eager forward on `stream` (first-use initialisation), then captures.  `stream` must not be the legacy
+ * default stream (CUDA cannot capture it); replays may go to any stream. */
+int b200q_graph_create(const b200q_static_net* net, const float* x_static, float* logits_static, int64_t b,
+                       void* workspace, int64_t workspace_bytes, int flags, void* stream, b200q_graph** out);
+int b200q_graph_launch(b200q_graph* g, void* stream);
+int b200q_graph_destroy(b200q_graph* g);
 
 /* Measurement hook (bench.py roofline): the same forward with a CUDA event recorded on `stream` before every layer
  * kernel and after the last one; synchronises on the last event and writes b200q_static_num_stages() per-kernel

@@ -104,18 +104,34 @@ def flatten_nchw(x_nhwc: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(x_nhwc.transpose(0, 3, 1, 2)).reshape(B, -1)
 
 
+SMALL_SCALE_THRESHOLD = F32(6.1e-5)
+
+
 def dynamic_qparams(mn: float, mx: float, qmin: int = 0, qmax: int = 127):
-    """fbgemm ChooseQuantizationParams(min, max, 0, qmax) with reduce_range (qmax=127)
-    as quantized::linear_dynamic calls it; fp32 scale, nudged zero-point."""
-    mn = min(float(mn), 0.0)
-    mx = max(float(mx), 0.0)
+    """ChooseQuantizationParams(min, max, 0, 255, reduce_range=True) (ATen/native/quantized/cpu/QuantUtils.h; not under
+    /root/reference - torch 2.11 is the de-facto pin) as quantized::linear_dynamic calls it: fp32 scale, nudged
+    zero-point.  Pinned against ``torch._choose_qparams_per_tensor`` in tests/test_oracle.py."""
+    mn = F32(min(F32(mn), F32(0.0)))
+    mx = F32(max(F32(mx), F32(0.0)))
     scale = (np.float64(mx) - np.float64(mn)) / (qmax - qmin)
-    if F32(scale) == 0.0 or np.isinf(1.0 / scale):
-        scale = 0.1
-    zp_from_min = qmin - mn / scale
-    zp_from_max = qmax - mx / scale
-    err_min = abs(qmin) + abs(mn / scale)
-    err_max = abs(qmax) + abs(mx / scale)
+    with np.errstate(divide="ignore", over="ignore"):
+        if F32(scale) == 0.0 or np.isinf(F32(1.0) / F32(scale)):
+            scale = np.float64(0.1)
+    if scale < np.float64(SMALL_SCALE_THRESHOLD):
+        org_scale = F32(scale)
+        scale = np.float64(SMALL_SCALE_THRESHOLD)
+        if mn == 0.0:
+            mx = F32(SMALL_SCALE_THRESHOLD * F32(qmax - qmin))
+        elif mx == 0.0:
+            mn = F32(-(SMALL_SCALE_THRESHOLD * F32(qmax - qmin)))
+        else:
+            amplifier = F32(SMALL_SCALE_THRESHOLD / org_scale)
+            mn = F32(mn * amplifier)
+            mx = F32(mx * amplifier)
+    zp_from_min = qmin - np.float64(mn) / scale
+    zp_from_max = qmax - np.float64(mx) / scale
+    err_min = abs(qmin) - abs(np.float64(mn) / scale)
+    err_max = abs(qmax) - abs(np.float64(mx) / scale)
     izp = zp_from_min if err_min < err_max else zp_from_max
     if izp < qmin:
         zp = qmin
@@ -162,3 +178,54 @@ def static_forward(x_f32_nchw: np.ndarray, qp: dict, taps: dict | None = None) -
                                np.asarray(L["bias"]), L["out_scale"], L["out_zp"], relu=relu))
         s, zp = L["out_scale"], L["out_zp"]
     return dequantize(x, s, zp)
+
+
+def histc(x: np.ndarray, bins: int, lo: float, hi: float) -> np.ndarray:
+    """torch.histc (ATen CPU, linear bins, no local search): bin = int(((x - lo) * bins) / (hi - lo)) evaluated in fp32
+    in that order; bin == bins -> bins - 1; values outside [lo, hi] are dropped; a degenerate range is widened by 1
+    on both sides.  Rule found by experiment against torch 2.11 (tests/test_oracle.py pins it)."""
+    lo, hi = F32(lo), F32(hi)
+    if lo == hi:
+        lo, hi = lo - F32(1), hi + F32(1)
+    x = np.asarray(x, dtype=F32).reshape(-1)
+    x = x[(x >= lo) & (x <= hi)]
+    pos = (((x - lo) * F32(bins)) / (hi - lo)).astype(np.int64)
+    pos[pos >= bins] = bins - 1
+    return np.bincount(pos, minlength=bins).astype(np.int64)
+
+
+def sandwich_lut(out_scale: float, out_zp: int, next_scale: float, next_zp: int) -> np.ndarray:
+    """DeQuantStub -> fp32 ReLU -> next QuantStub as a uint8 -> uint8 table (custom variant as intended,
+    ``models/custom_quantization_model.py:34-58``): lut[q] = quantize(max(dequantize(q), 0))."""
+    v = np.maximum(dequantize(np.arange(256, dtype=np.uint8), out_scale, out_zp), F32(0.0))
+    return quantize_per_tensor(v, next_scale, next_zp)
+
+
+def sandwich_forward(x_f32_nchw: np.ndarray, sp: dict, taps: dict | None = None) -> np.ndarray:
+    """The per-layer sandwich net in integers (call order of ``models/custom_quantization_model.py:233-261``):
+    ``sp[layer]`` = {in_scale, in_zp, w_int8, w_scales, bias, out_scale, out_zp} for conv1..conv6 and fc1, ``sp["fc2"]``
+    = {weight, bias} fp32.  ReLU / max-pool between the sandwiches run on the quantized values through the monotone
+    boundary table (equal to running them in fp32 on the dequantised tensors).  Returns fp32 logits; taps[layer] = uint8
+    NHWC output of each int8 layer, before ReLU."""
+    names = ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "fc1")
+    x = np.ascontiguousarray(np.asarray(x_f32_nchw, dtype=F32).transpose(0, 2, 3, 1))
+    L = sp["conv1"]
+    a = quantize_per_tensor(x, L["in_scale"], L["in_zp"])
+    for i, name in enumerate(names[:6]):
+        L = sp[name]
+        a = conv2d_q(a, L["in_scale"], L["in_zp"], np.asarray(L["w_int8"]), np.asarray(L["w_scales"]),
+                     np.asarray(L["bias"]), L["out_scale"], L["out_zp"], relu=False)
+        if taps is not None:
+            taps[name] = a
+        nxt = sp[names[i + 1]]
+        a = sandwich_lut(L["out_scale"], L["out_zp"], nxt["in_scale"], nxt["in_zp"])[a]
+        if i % 2 == 1:
+            a = max_pool2x2(a)
+    L = sp["fc1"]
+    h = linear_q(flatten_nchw(a), L["in_scale"], L["in_zp"], np.asarray(L["w_int8"]), np.asarray(L["w_scales"]),
+                 np.asarray(L["bias"]), L["out_scale"], L["out_zp"], relu=False)
+    if taps is not None:
+        taps["fc1"] = h
+    hf = np.maximum(dequantize(h, L["out_scale"], L["out_zp"]), F32(0.0))
+    return (hf.astype(np.float64) @ np.asarray(sp["fc2"]["weight"], dtype=np.float64).T
+            + np.asarray(sp["fc2"]["bias"], dtype=np.float64)).astype(F32)

@@ -132,3 +132,107 @@ def extract_qparams(qmodel: nn.Module) -> dict:
             "out_zp": int(mod.zero_point),
         }
     return out
+
+
+# ------------------------------------------------------------------ dynamic PTQ (as written in the reference)
+def build_dynamic_oracle(fp32_net: nn.Module) -> nn.Module:
+    """What ``DynamicPTQModel.quantize`` (``models/dynamic_ptq_model.py:281-308``) builds: BN folded, then
+    ``quantize_dynamic({Linear, Conv2d}, qint8)`` - which converts fc1 / fc2 only."""
+    torch.backends.quantized.engine = "fbgemm"
+    fused = fuse_modules(copy.deepcopy(fp32_net).cpu().eval(), FUSE_LIST, inplace=False)
+    return torch.ao.quantization.quantize_dynamic(fused, {nn.Linear, nn.Conv2d}, dtype=torch.qint8).eval()
+
+
+# ------------------------------------------------------------------ the custom variant "as intended" (sandwiches)
+SANDWICH_LAYERS = ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "fc1")
+
+
+class _Sandwich(nn.Module):
+    """``CustomQuantizedConv2d`` / ``CustomQuantizedLinear`` (``models/custom_quantization_model.py:34-58``)."""
+
+    def __init__(self, layer):
+        super().__init__()
+        self.quant = QuantStub()
+        self.dequant = DeQuantStub()
+        self.layer = layer
+
+    def forward(self, x):
+        return self.dequant(self.layer(self.quant(x)))
+
+
+class SandwichWrap(nn.Module):
+    """``CustomQuantizedSimpleConvNet`` (``models/custom_quantization_model.py:202-261``) in the one form in which
+    ``prepare``/``convert`` can be applied to it (survey probe P3): no outer QuantStub/DeQuantStub (they double-quantise,
+    SURVEY F5), ``reshape`` instead of ``view``, ``fc2`` fp32 (``:219``); dropout is identity in eval."""
+
+    def __init__(self, fused: nn.Module):
+        super().__init__()
+        for name in SANDWICH_LAYERS:
+            setattr(self, name, _Sandwich(getattr(fused, name)))
+        self.fc2 = fused.fc2
+        self.fc2.qconfig = None
+
+    def forward(self, x, taps: dict | None = None):
+        def run(name, t):
+            sw = getattr(self, name)
+            q = sw.layer(sw.quant(t))
+            if taps is not None:
+                taps[name] = q
+            return F.relu(sw.dequant(q))
+
+        x = run("conv2", run("conv1", x))
+        x = F.max_pool2d(x, 2, 2)
+        x = run("conv4", run("conv3", x))
+        x = F.max_pool2d(x, 2, 2)
+        x = run("conv6", run("conv5", x))
+        x = F.max_pool2d(x, 2, 2)
+        x = run("fc1", x.reshape(-1, 256 * 4 * 4))
+        return self.fc2(x)
+
+
+def build_sandwich_oracle(fp32_net: nn.Module, calib_batches) -> nn.Module:
+    torch.backends.quantized.engine = "fbgemm"
+    fused = fuse_modules(copy.deepcopy(fp32_net).cpu().eval(), FUSE_LIST, inplace=False)
+    w = SandwichWrap(fused).eval()
+    w.qconfig = get_default_qconfig("fbgemm")
+    w.fc2.qconfig = None
+    p = prepare(w, inplace=False)
+    nthreads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        with torch.no_grad():
+            for xb in calib_batches:
+                p(xb)
+    finally:
+        torch.set_num_threads(nthreads)
+    return convert(p, inplace=False).eval()
+
+
+@torch.no_grad()
+def run_sandwich_oracle(qmodel: nn.Module, x: torch.Tensor):
+    """``(logits fp32 [B,10], taps)``; taps[name] = uint8 output of the sandwich's int8 layer (pre-ReLU), logical
+    NCHW / [B,F] order."""
+    torch.backends.quantized.engine = "fbgemm"
+    taps: dict = {}
+    logits = qmodel(x.cpu(), taps)
+    return logits, {k: v.int_repr() for k, v in taps.items()}
+
+
+def sandwich_activation_qparams(qmodel: nn.Module) -> dict:
+    """``{layer: (in_scale, in_zp, out_scale, out_zp)}`` of a converted sandwich model."""
+    out = {}
+    for name in SANDWICH_LAYERS:
+        sw = getattr(qmodel, name)
+        out[name] = (float(sw.quant.scale), int(sw.quant.zero_point), float(sw.layer.scale), int(sw.layer.zero_point))
+    return out
+
+
+def override_sandwich_qparams(qmodel: nn.Module, act: dict) -> nn.Module:
+    """Frozen activation qparams (see ``override_activation_qparams``) for the sandwich model."""
+    for name in SANDWICH_LAYERS:
+        s_in, z_in, s_out, z_out = act[name]
+        sw = getattr(qmodel, name)
+        sw.quant.scale.fill_(float(s_in))
+        sw.quant.zero_point.fill_(int(z_in))
+        sw.layer.scale, sw.layer.zero_point = float(s_out), int(z_out)
+    return qmodel

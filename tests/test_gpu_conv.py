@@ -238,9 +238,10 @@ def test_conv_tc_many_bands_per_cta(qparams, qparams_np, name, b, pool):
 
 
 def test_alternate_instantiations_stay_bit_exact():
-    """The A-B switches select other template instantiations of the same kernels (16 epilogue warps x 8 channels in the
-    halo kernels, the fused conv1+conv2 kernel in the forward); they are read once per process, so they are exercised in
-    a child process: whole-net logits must equal the default configuration's bit for bit."""
+    """The A-B switches of the DEVELOPMENT library select other template instantiations of the same kernels (16 epilogue
+    warps x 8 channels in the halo kernels, the fused conv1+conv2 kernel, the generic shifted-TMA kernel for every
+    conv); they are read once per process, so they are exercised in a child process: whole-net logits must equal the
+    product configuration's bit for bit.  The product library must ignore every such variable."""
     import subprocess
     import sys
     code = (
@@ -252,10 +253,84 @@ def test_alternate_instantiations_stay_bit_exact():
         "import hashlib; print(hashlib.sha256(y.cpu().numpy().tobytes()).hexdigest())\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     digests = {}
-    for name, env in (("default", {}), ("ew16", {"B200Q_HALO_EW": "16"}), ("fuse12", {"B200Q_FUSE12": "1"})):
+    from convnet_quantization_b200 import _lib
+    dev = str(_lib.build(dev=True))  # the switches exist in the development library only (-DB200Q_DEV)
+    for name, env in (("default", {}), ("dev", {"B200Q_LIB": dev}), ("ew16", {"B200Q_LIB": dev, "B200Q_HALO_EW": "16"}),
+                      ("fuse12", {"B200Q_LIB": dev, "B200Q_FUSE12": "1"}), ("no_halo", {"B200Q_LIB": dev, "B200Q_NO_HALO": "1"}),
+                      ("ignored", {"B200Q_HALO_DEBUG": "14", "B200Q_PAIR_DEBUG": "46", "B200Q_NO_HALO": "1"})):
         e = dict(os.environ)
         e.update(env)
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, cwd=root, timeout=600)
         assert r.returncode == 0, f"{name}: {r.stderr[-1500:]}"
         digests[name] = r.stdout.strip().splitlines()[-1]
-    assert digests["ew16"] == digests["default"] and digests["fuse12"] == digests["default"], digests
+    assert len(set(digests.values())) == 1, digests  # "ignored": the product library has no such switches
+
+
+@pytest.mark.parametrize("name,pool", [("conv2", False), ("conv2", True), ("conv3", False), ("conv4", False), ("conv4", True),
+                                       ("conv5", False), ("conv6", False), ("conv6", True)])
+@pytest.mark.parametrize("b", [2, 37])
+def test_conv_tc_without_host_mirrors(qparams, qparams_np, name, pool, b):
+    """Documented ABI branch (include/b200q.h, b200q_requant.mult_host): with corr_host / mult_host / bdiv_host NULL the
+    kernels that take their constants as kernel parameters are not eligible and b200q_conv3x3_tc must run the
+    shifted-TMA kernel that stages the DEVICE tables through shared memory (igemm_tc.cu, nine border classes) - all
+    five geometries, pool on and off."""
+    import ctypes as C
+    from convnet_quantization_b200 import _lib
+    from oracle import int_ops as IO
+    pc, s, zp = _packed(qparams, name)
+    bare = _lib.Conv3x3.from_buffer_copy(pc.c)
+    bare.corr_host = None
+    bare.rq.mult_host = None
+    bare.rq.bdiv_host = None
+    x = _rand_u8((b, pc.img, pc.img, pc.cin), 31 * b + len(name)).cuda()
+    o = pc.img // 2 if pool else pc.img
+    y = torch.empty((b, o, o, pc.cout), dtype=torch.uint8, device="cuda")
+    lib = _lib.load()
+    n0 = lib.b200q_launch_count()
+    _lib.check(lib.b200q_conv3x3_tc(x.data_ptr(), y.data_ptr(), b, C.byref(bare), int(pool),
+                                    torch.cuda.current_stream().cuda_stream), "conv3x3_tc")
+    torch.cuda.synchronize()
+    assert lib.b200q_launch_count() == n0 + 1
+    want = _want_conv(x.cpu().numpy(), s, zp, qparams_np[name])
+    if pool:
+        want = IO.max_pool2x2(want)
+    assert np.array_equal(y.cpu().numpy(), want)
+    # same answer as the default (host-mirror) kernels
+    from convnet_quantization_b200 import ops
+    assert torch.equal(ops.conv2d_q(x, pc, pool2x2=pool), y)
+
+
+@pytest.mark.parametrize("b,k,n,relu", [(1, 4096, 512, True), (127, 4096, 512, False), (128, 4096, 512, True),
+                                         (300, 4096, 512, False), (1, 512, 10, False), (129, 512, 10, False),
+                                         (1000, 512, 10, True), (40, 1024, 16, False)])
+def test_linear_dynamic_tensor_core(b, k, n, relu):
+    """quantized::linear_dynamic on the tensor cores (quantising producer, fp32 epilogue) vs the live torch op:
+    partial / several / many 128-row tiles, both N tiles (512 = two accumulators, <= 16 = TMA zero-filled rows)."""
+    from convnet_quantization_b200 import ops
+    from oracle import int_ops as IO
+    torch.backends.quantized.engine = "fbgemm"
+    g = torch.Generator().manual_seed(b + k + n)
+    lin = torch.nn.Linear(k, n)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(n, k, generator=g) * 0.05)
+        lin.bias.copy_(torch.randn(n, generator=g) * 0.1)
+    qlin = torch.ao.quantization.quantize_dynamic(torch.nn.Sequential(lin), {torch.nn.Linear}, dtype=torch.qint8)[0]
+    x = torch.randn(b, k, generator=g) * 0.7 + 0.2
+    want = qlin(x)
+    if relu:
+        want = torch.relu(want)
+    w = qlin.weight()
+    dw = ops.DynamicLinearWeights(w.int_repr(), w.q_scale(), qlin.bias(), "cuda")
+    for _ in range(2):  # twice: the scratch counter must self-reset
+        got = ops.linear_dynamic(x.cuda(), dw, relu=relu).cpu()
+        torch.testing.assert_close(got, want, rtol=1e-3, atol=1e-3 * float(want.abs().max()))
+    # the activation qparams the kernel used are the ATen ones, and against the integer restatement fed the SAME
+    # quantised activations the result is exact up to the fp32 output rounding
+    qp = dw.last_qparams().cpu()
+    s, z = torch._choose_qparams_per_tensor(x, True)
+    assert qp[2].item() == np.float32(s) and int(qp[4]) == z
+    mine = IO.linear_dynamic(x.numpy(), w.int_repr().numpy(), w.q_scale(), qlin.bias().detach().numpy())
+    if relu:
+        mine = np.maximum(mine, 0)
+    np.testing.assert_allclose(got.numpy(), mine, rtol=1e-5, atol=1e-5 * np.abs(mine).max())
+    assert tuple(ops.linear_dynamic(x[:0].cuda(), dw).shape) == (0, n)

@@ -82,3 +82,77 @@ def test_errors_are_exceptions():
         ops.max_pool2d_q(torch.zeros(1, 3, 3, 16, dtype=torch.uint8, device="cuda"))  # odd h/w
     with pytest.raises(_lib.B200QError):
         ops.relu_q(torch.zeros(16, dtype=torch.uint8), 3)  # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("case", ["zeros", "tiny", "tiny_pos", "tiny_neg", "neg_only", "pos_only", "mixed", "huge"])
+def test_dynamic_qparams_edge_cases_vs_torch(case):
+    """The device port of ChooseQuantizationParams (small-scale cut-off, one-sided and degenerate ranges)
+    against torch's own binding of the ATen routine."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(len(case))
+    x = {"zeros": torch.zeros(1000), "tiny": torch.randn(1000, generator=g) * 1e-6,
+         "tiny_pos": torch.rand(1000, generator=g) * 3e-4, "tiny_neg": -torch.rand(1000, generator=g) * 3e-4,
+         "neg_only": -torch.rand(1000, generator=g) - 0.5, "pos_only": torch.rand(1000, generator=g) + 0.5,
+         "mixed": torch.randn(1000, generator=g) * 2.0, "huge": torch.randn(1000, generator=g) * 1e30}[case]
+    out = ops.minmax(x.cuda()).cpu()
+    s, z = torch._choose_qparams_per_tensor(x, True)
+    assert out[2].item() == np.float32(s) and int(out[4]) == z, (case, out.tolist(), s, z)
+    assert out[0].item() == min(float(x.min()), 0.0) and out[1].item() == max(float(x.max()), 0.0)
+
+
+@pytest.mark.parametrize("n", [1, 7, 4096, 1000003])
+def test_aminmax(n):
+    ops = _ops()
+    x = torch.randn(n, generator=torch.Generator().manual_seed(n)) * 3 + 5.0  # strictly positive for small n: no zero extension
+    out = ops.aminmax(x.cuda()).cpu()
+    mn, mx = torch.aminmax(x)
+    assert out[0] == mn and out[1] == mx
+
+
+@pytest.mark.parametrize("n,bins", [(1, 2048), (1000, 2048), (300007, 2048), (4 * 1000 * 1000, 2048), (50000, 37), (50000, 4096)])
+def test_histc_equals_torch_cpu(n, bins):
+    """b200q_histc == torch.histc on the CPU (the HistogramObserver's counts), incl. values on the bin edges, half the
+    tensor in one bin (post-ReLU zeros), a widened range and out-of-range values."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n + bins)
+    x = torch.relu(torch.randn(n, generator=g) * 1.3)
+    lo, hi = float(x.min()), float(x.max())
+    for a, b in ((lo, hi), (lo - 0.37, hi * 1.21 + 0.1), (0.1, max(hi * 0.5, 0.2))):
+        want = torch.histc(x, bins, min=a, max=b).to(torch.int64)
+        got = ops.histc(x.cuda(), bins, a, b).cpu()
+        assert torch.equal(got, want), (a, b, int((got - want).abs().sum()))
+    k = torch.randint(0, bins + 1, (n,), generator=g).float()
+    edges = (-1.5 + 4.0 * k / bins).float()
+    assert torch.equal(ops.histc(edges.cuda(), bins, -1.5, 2.5).cpu(), torch.histc(edges, bins, min=-1.5, max=2.5).to(torch.int64))
+    same = torch.full((max(n, 4),), 2.5)
+    assert torch.equal(ops.histc(same.cuda(), bins, 2.5, 2.5).cpu(), torch.histc(same, bins, min=2.5, max=2.5).to(torch.int64))
+
+
+@pytest.mark.parametrize("n", [3, 16, 100003, 8 * 1000 * 1000])
+def test_lut_u8(n):
+    ops = _ops()
+    g = torch.Generator().manual_seed(n)
+    x = torch.randint(0, 256, (n,), dtype=torch.uint8, generator=g)
+    lut = torch.randint(0, 256, (256,), dtype=torch.uint8, generator=g)
+    got = ops.lut_u8(x.cuda(), lut).cpu()
+    assert torch.equal(got, lut[x.long()])
+
+
+def test_histogram_observer_on_gpu_equals_cpu_observer():
+    """the GPU-side observer must leave exactly the state (histogram, min, max) and the qparams torch's
+    CPU HistogramObserver derives from the same tensors - first observation, same-range update, widened range."""
+    from convnet_quantization_b200 import ptq
+    g = torch.Generator().manual_seed(11)
+    batches = [torch.relu(torch.randn(64, 64, 16, 16, generator=g) * s + m) for s, m in ((1.0, 0.2), (0.5, 0.1), (2.5, -0.3), (1.0, 0.0))]
+    cpu = torch.ao.quantization.HistogramObserver(reduce_range=True)
+    gpu = ptq.B200HistogramObserver(reduce_range=True)
+    gpu = gpu.cuda()  # must stay on the host
+    assert not gpu.histogram.is_cuda
+    for xb in batches:
+        cpu(xb)
+        gpu(xb.cuda())
+        assert torch.equal(cpu.histogram, gpu.histogram)
+        assert cpu.min_val == gpu.min_val and cpu.max_val == gpu.max_val
+    s0, z0 = cpu.calculate_qparams()
+    s1, z1 = gpu.calculate_qparams()
+    assert torch.equal(s0, s1) and torch.equal(z0, z1)

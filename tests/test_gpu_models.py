@@ -180,3 +180,114 @@ def test_drivers_protocol(sd):
     assert top1 > 60.0 and top5 >= top1  # labels are the fp32 argmax; int8 agrees on most images
     thr = InferenceBenchmark(loader, device="cuda").measure_throughput(q, batch_size=32, num_iterations=20, verbose=False)
     assert thr > 0
+
+
+def test_custom_sandwich_vs_reference_golden(golden, sd, fp32_net):
+    """the custom variant as intended (per-layer QuantStub -> int8 -> DeQuantStub, fp32 ReLU / pool,
+    fc2 fp32).  Every int8 layer output bit-exact against (a) the golden taken from the REFERENCE's own wrapper class
+    (tests/golden/make_golden_sandwich.py) and (b) the live converted torch model; logits within 1e-3 (fc2 is an fp32
+    GEMM on both sides) with identical argmax."""
+    import hashlib
+    from convnet_quantization_b200 import ptq, synth
+    from convnet_quantization_b200.models._gpu_modules import B200SandwichQuantizedNet
+    from convnet_quantization_b200.models.custom_quantization_model import CustomQuantizationModel
+    from oracle import torch_oracle as TO
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sandwich_golden.npz"))
+    x = _x(golden)
+    assert np.array_equal(g["x_u8"], golden["x_u8"])
+    # (a) golden activation qparams pinned (calibration is fp32 CPU work), weights from the product's own calibration
+    sp = ptq.calibrate_sandwich(fp32_net, synth.calibration_batches())
+    for n in TO.SANDWICH_LAYERS:
+        sp[n]["in_scale"], sp[n]["in_zp"] = float(g[f"{n}_qparams"][0]), int(g[f"{n}_qparams"][1])
+        sp[n]["out_scale"], sp[n]["out_zp"] = float(g[f"{n}_qparams"][2]), int(g[f"{n}_qparams"][3])
+    net = B200SandwichQuantizedNet(sp, "cuda")
+    logits, taps = net.forward_with_taps(x)
+    for n in TO.SANDWICH_LAYERS:
+        a = np.ascontiguousarray(taps[n].cpu().numpy())
+        assert hashlib.sha256(a.tobytes()).hexdigest() == str(g[f"sandwich_{n}_sha"]), n
+    want = g["sandwich_logits"]
+    np.testing.assert_allclose(logits.cpu().numpy(), want, rtol=1e-3, atol=1e-3 * np.abs(want).max())
+    assert np.array_equal(logits.cpu().numpy().argmax(1), want.argmax(1))
+    fused = net(x)  # production route: pools fused into conv2/4/6, tables on the pooled tensors; CPU in -> CPU out
+    assert not fused.is_cuda and torch.equal(fused, logits.cpu())
+    # (b) through the model class, against the live oracle calibrated on this host; odd batch, saturating inputs
+    cm = CustomQuantizationModel(mode="sandwich")
+    cm.load_state_dict(sd)
+    q = cm.quantize()
+    assert q.is_custom_quantized and cm.is_custom_quantized
+    oq = TO.build_sandwich_oracle(fp32_net, synth.calibration_batches())
+    xb = synth.images_f32(37, seed=8) * 2.5
+    want_l, want_t = TO.run_sandwich_oracle(oq, xb)
+    got_l, got_t = q.forward_with_taps(xb)
+    for n in TO.SANDWICH_LAYERS:
+        w = want_t[n].numpy()
+        w = w.transpose(0, 2, 3, 1) if w.ndim == 4 else w
+        assert np.array_equal(got_t[n].cpu().numpy(), w), n
+    torch.testing.assert_close(got_l.cpu(), want_l, rtol=1e-3, atol=1e-3 * float(want_l.abs().max()))
+    assert torch.equal(cm(xb.cuda()).cpu(), got_l.cpu())
+    assert tuple(q(xb[:0]).shape) == (0, 10)
+
+
+def test_gpu_side_calibration(sd, fp32_net, oracle_model):
+    """``StaticPTQModel.quantize(loader, calibration_device='cuda')`` runs the calibration forward and
+    the observers' reductions on the GPU.  The observers are exact (test_histogram_observer_on_gpu_equals_cpu_observer);
+    what differs from host calibration is the fp32 conv arithmetic that feeds them (cuDNN vs MKL-DNN summation order),
+    so the resulting activation scales agree to ~1e-4 relative, the weights are identical, and the model built from
+    them is bit-exact against the torch oracle GIVEN THOSE qparams."""
+    from convnet_quantization_b200 import synth
+    from convnet_quantization_b200.models.static_ptq_model import StaticPTQModel
+    from oracle import torch_oracle as TO
+    m = StaticPTQModel()
+    m.fp32_model.load_state_dict(sd)
+    loader = [(b, torch.zeros(b.shape[0], dtype=torch.long)) for b in synth.calibration_batches()]
+    q = m.quantize(loader, calibration_device="cuda")
+    host = TO.extract_qparams(oracle_model)
+    qp = m.qparams
+    assert abs(qp["in_scale"] / host["in_scale"] - 1) < 1e-6 and qp["in_zp"] == host["in_zp"]  # input: same tensor on both
+    for n in ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "fc1", "fc2"):
+        assert torch.equal(qp[n]["w_int8"], host[n]["w_int8"]) and torch.equal(qp[n]["w_scales"], host[n]["w_scales"])
+        assert abs(qp[n]["out_scale"] / host[n]["out_scale"] - 1) < 5e-3, (n, qp[n]["out_scale"], host[n]["out_scale"])
+        assert abs(qp[n]["out_zp"] - host[n]["out_zp"]) <= 1, n
+    import copy
+    oq = copy.deepcopy(oracle_model)
+    act = {"in": (qp["in_scale"], qp["in_zp"])}
+    act.update({n: (qp[n]["out_scale"], qp[n]["out_zp"]) for n in ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "fc1", "fc2")})
+    TO.override_activation_qparams(oq, act)
+    x = synth.images_f32(64, seed=12)
+    assert torch.equal(q(x), TO.run_static_oracle(oq, x)[0])
+
+
+def test_forward_synchronises_and_int_device(sd):
+    """The drop-in modules finish the work before returning for CUDA inputs (the reference's benchmark reads the wall
+    clock right after ``model(data)``); ``sync_on_forward = False`` opts out.  ``model.to(0)`` is ``model.to('cuda:0')``."""
+    from convnet_quantization_b200 import synth
+    from convnet_quantization_b200.models.static_ptq_model import StaticPTQModel
+    m = StaticPTQModel()
+    m.fp32_model.load_state_dict(sd)
+    q = m.quantize()
+    x = synth.images_f32(4096, seed=1).cuda()
+    q(x)
+    torch.cuda.synchronize()
+    q(x)
+    assert torch.cuda.current_stream().query(), "forward returned with work still queued"
+    q.sync_on_forward = False
+    q(x)
+    pending = not torch.cuda.current_stream().query()
+    torch.cuda.synchronize()
+    assert pending, "opt-out must leave the forward asynchronous"
+    q.sync_on_forward = True
+    assert q.to(0) is q and q.engine_device == torch.device("cuda", 0)
+    assert q.cuda(0) is q and q.cpu() is q and q.to("cpu") is q and q.to(torch.float32) is q
+    if torch.cuda.device_count() > 1:
+        q.to(1)
+        assert q.engine_device == torch.device("cuda", 1)
+        q.to(0)
+
+
+def test_dynamic_net_empty_batch(sd):
+    from convnet_quantization_b200.models.dynamic_ptq_model import DynamicPTQModel
+    m = DynamicPTQModel()
+    m.load_state_dict(sd)
+    m.quantize()
+    assert tuple(m(torch.empty(0, 3, 32, 32)).shape) == (0, 10)
+    assert tuple(m(torch.empty(0, 3, 32, 32, device="cuda")).shape) == (0, 10)

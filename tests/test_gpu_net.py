@@ -82,7 +82,7 @@ def test_empty_batch(engine):
 
 
 @pytest.mark.parametrize("b", [1, 5, 300])
-def test_uint8_data_path_is_bit_identical(engine, b):
+def test_uint8_data_path_is_bit_identical(engine, oracle_model, b):
     """Raw uint8 NHWC pixels through the look-up-table quantiser == the fp32 route (ToTensor + Normalize on the CPU, then
     QuantStub), logits bit for bit."""
     from convnet_quantization_b200 import synth
@@ -90,10 +90,13 @@ def test_uint8_data_path_is_bit_identical(engine, b):
     pix = torch.randint(0, 256, (b, 32, 32, 3), dtype=torch.uint8, generator=g)
     pix[0, :4] = 0
     pix[0, 4:8] = 255
-    want = engine.forward(synth.normalize(pix.permute(0, 3, 1, 2)).contiguous().cuda())
+    x = synth.normalize(pix.permute(0, 3, 1, 2)).contiguous()
+    want = engine.forward(x.cuda())
     got = engine.forward_u8(pix.cuda())
     torch.cuda.synchronize()
     assert torch.equal(got, want)
+    from oracle import torch_oracle as TO
+    assert torch.equal(got.cpu(), TO.run_static_oracle(oracle_model, x)[0])  # and directly against the CPU oracle
 
 
 def test_uint8_data_path_host_pipeline(golden_qparams):
@@ -123,3 +126,108 @@ def test_second_device_in_the_same_process(golden_qparams):
         y1 = e1.forward(x.to("cuda:1")).cpu()
     y0b = e0.forward(x.to("cuda:0")).cpu()
     assert torch.equal(y0, y1) and torch.equal(y0, y0b)
+
+
+def _oracle_sample(n: int, count: int) -> torch.Tensor:
+    """``count`` image indices of a batch of ``n``: first and last 128 (tile / band / chunk boundaries) + a stride."""
+    idx = torch.cat([torch.arange(min(128, n)), torch.arange(max(n - 128, 0), n), torch.arange(0, n, max(1, n // count))])
+    return torch.unique(idx)
+
+
+@pytest.mark.parametrize("n", [16384, 65536])
+def test_benchmarked_batches_are_bit_exact_vs_oracle(engine, oracle_model, qparams, n):
+    """BASELINE config 2 at the sizes bench.py times (16 384 per step; 65 536 = top of the sweep): >= 1 024 images of the
+    batch - first, last, strided - against the fbgemm CPU oracle, through engine.forward AND through the drop-in module
+    fed HOST tensors (chunked two-stream pipeline), plus whole-batch consistency of the two routes."""
+    from convnet_quantization_b200 import synth
+    from convnet_quantization_b200.models._gpu_modules import B200StaticQuantizedNet
+    from oracle import torch_oracle as TO
+    x = synth.images_f32(n, seed=1000 + n)
+    idx = _oracle_sample(n, 1024)
+    assert idx.numel() >= 1024
+    want, _ = TO.run_static_oracle(oracle_model, x[idx])
+    got = engine.forward(x.cuda())
+    torch.cuda.synchronize()
+    assert tuple(got.shape) == (n, 10)
+    assert torch.equal(got.cpu()[idx], want)
+    qmodel = B200StaticQuantizedNet(qparams, "cuda")
+    host = qmodel(x)  # CPU input -> CPU logits
+    assert not host.is_cuda and torch.equal(host, got.cpu())
+
+
+@pytest.mark.parametrize("b", [1, 2, 7, 32, 128, 500])
+@pytest.mark.parametrize("pdl", [True, False])
+def test_graph_executor_is_bit_exact(qparams, oracle_model, b, pdl):
+    """Whole-network executor: CUDA-graph replay with / without programmatic dependent launch ==
+    eager launches == CPU oracle, across replays with DIFFERENT contents in the captured buffer (stale data from an
+    overlapped predecessor kernel would show up here) and when replays are issued back to back."""
+    from convnet_quantization_b200 import synth
+    from convnet_quantization_b200.engine import StaticEngine
+    from oracle import torch_oracle as TO
+    eng = StaticEngine(qparams, "cuda", pdl=pdl)
+    buf = torch.empty(b, 3, 32, 32, device="cuda")
+    outs = []
+    for rep in range(4):
+        x = synth.images_f32(b, seed=50 * b + rep) * (3.0 if rep == 2 else 1.0)
+        buf.copy_(x)
+        y = eng.forward(buf)  # rep 0: eager (first sighting), rep 1: capture + replay, rep 2..: replay
+        want, _ = TO.run_static_oracle(oracle_model, x)
+        assert torch.equal(y.cpu(), want), (b, rep)
+        assert torch.equal(eng.forward(buf, graph=False), y)
+        outs.append(y)
+    assert len(eng._graphs) == 1
+    out = torch.empty(b, 10, device="cuda")
+    for rep in range(3):  # (batch, input, output) keyed graph: writes straight into the caller's buffer
+        assert eng.forward(buf, out=out) is out
+    assert torch.equal(out, outs[-1])
+    ys = [eng.forward(buf) for _ in range(20)]  # back-to-back replays (each clones the static logits)
+    torch.cuda.synchronize()
+    assert all(torch.equal(y, outs[-1]) for y in ys)
+
+
+def test_graph_executor_launch_accounting_and_cache(qparams):
+    from convnet_quantization_b200 import _lib, synth
+    from convnet_quantization_b200.engine import StaticEngine
+    lib = _lib.load()
+    eng = StaticEngine(qparams, "cuda")
+    x = synth.images_f32(8, seed=1).cuda()
+    eng.forward(x)
+    eng.forward(x)
+    n0 = lib.b200q_launch_count()
+    for _ in range(5):
+        eng.forward(x)
+    assert lib.b200q_launch_count() - n0 == 5 * 8  # replays are counted like the eight launches they stand for
+    for i in range(StaticEngine.GRAPH_CACHE + 3):  # more distinct buffers than the cache holds: LRU, no growth
+        xi = synth.images_f32(3, seed=i).cuda()
+        eng.forward(xi)
+        eng.forward(xi)
+    assert len(eng._graphs) == StaticEngine.GRAPH_CACHE
+    big = synth.images_f32(StaticEngine.GRAPH_MAX_BATCH + 1, seed=2).cuda()
+    eng.forward(big)
+    eng.forward(big)
+    assert all(k[0] <= StaticEngine.GRAPH_MAX_BATCH for k in eng._graphs)
+    eng.release()
+    assert not eng._graphs and not eng._ws
+
+
+def test_engine_rejects_foreign_tensors(qparams):
+    """wrong device / dtype / shape / stride must raise, not fault."""
+    from convnet_quantization_b200 import _lib
+    from convnet_quantization_b200.engine import StaticEngine
+    eng = StaticEngine(qparams, "cuda")
+    x = torch.zeros(4, 3, 32, 32, device="cuda")
+    with pytest.raises(_lib.B200QError):
+        eng.forward(torch.zeros(4, 3, 32, 32))
+    with pytest.raises(_lib.B200QError):
+        eng.forward(x, out=torch.zeros(4, 10))
+    with pytest.raises(_lib.B200QError):
+        eng.forward(x, out=torch.zeros(4, 10, device="cuda", dtype=torch.float64))
+    with pytest.raises(_lib.B200QError):
+        eng.forward(x, out=torch.zeros(5, 10, device="cuda"))
+    with pytest.raises(_lib.B200QError):
+        eng.forward(x, out=torch.zeros(4, 20, device="cuda")[:, ::2])
+    with pytest.raises(_lib.B200QError):
+        eng.forward_u8(torch.zeros(4, 32, 32, 3, device="cuda"))  # fp32 where uint8 is expected
+    if torch.cuda.device_count() > 1:
+        with pytest.raises(_lib.B200QError):
+            eng.forward(torch.zeros(4, 3, 32, 32, device="cuda:1"))
