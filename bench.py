@@ -231,6 +231,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the quantized forward has no CPU fallback; use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: pin this rank to the CPUs next to its GPU before any pinned staging buffer is allocated
+    from convnet_quantization_b200 import sharding as _sh
+    host_binding = _sh.gpu_numa_info(local) if args.no_bind else _sh.bind_to_gpu_numa(local)
     # The contract is ONE JSON line on stdout.  NCCL prints its version banner on the C-level stdout when the first
     # communicator is created, so everything but that line is routed to stderr: fd 1 is pointed at fd 2 for the whole
     # run and the line is written to a private duplicate of the original stdout at the end (emit_line).
@@ -427,7 +430,8 @@ def run_ours(args):
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": "static-PTQ int8 SimpleConvNet forward, CIFAR-10 shape fp32 [B,3,32,32] -> logits [B,10]",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-sharded x{world}",
-                       "l2": f"input {x.numel() * 4 / 2**20:.0f} MiB + activations > 126 MiB L2 (no flush needed)"},
+                       "l2": f"input {x.numel() * 4 / 2**20:.0f} MiB + activations > 126 MiB L2 (no flush needed)",
+                       "host_binding_rank0": host_binding},
             "clocks": clocks.summary(), "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": launches, "roofline": roofline,
             "sustained": sustained, "parity": parity, "cpu_baseline": cpu_baseline,
             "eval": {"top1": counts[0], "top5": counts[1], "total": counts[2], "labels": "random (collective exercise only)"},
@@ -591,6 +595,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16384, help="images per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="do not pin the rank to its GPU's NUMA-local CPUs")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run oracle comparison (timing experiments)")
     ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of the extra sustained loop (0: skip)")
     ap.add_argument("--variant", default="static", choices=["static", "dynamic", "fp32", "custom", "custom_sandwich"],

@@ -27,14 +27,18 @@ constexpr int TC_TMA_WARP = TC_EPI_WARPS, TC_MMA_WARP = TC_EPI_WARPS + 1;
 constexpr int TILE_M = 128;
 constexpr int SMEM_BUDGET = 222 * 1024;
 
-template <int IMG, int CIN, int COUT, bool B_RESIDENT, bool POOL>
+// NT: N tile (accumulator columns per CTA tile); 0 = the widest that fits (min(COUT, 256)).  NT = 64 is the SMALL-BATCH
+// shape: a layer is cut into COUT/64 times more CTA tiles, so that a handful of images still spreads over many SMs (the
+// whole-network executor, net.cu b200q_graph_*: at batch 1 every layer is a chain of dependent L2 round trips, and the
+// only lever is how little each CTA has to stream).
+template <int IMG, int CIN, int COUT, bool B_RESIDENT, bool POOL, int NT = 0>
 struct TcCfg {
   static constexpr bool CONV = IMG > 0;
   static constexpr int KC = (CIN % 128 == 0) ? 128 : 64;  // K-chunk bytes == swizzle span
   static constexpr int TAPS = CONV ? 9 : 1;
   static constexpr int CHUNKS_PER_TAP = CIN / KC;
   static constexpr int NCHUNK = TAPS * CHUNKS_PER_TAP;
-  static constexpr int N_TILE = COUT > 256 ? 256 : COUT;
+  static constexpr int N_TILE = NT > 0 ? NT : (COUT > 256 ? 256 : COUT);
   static constexpr int N_TILES = COUT / N_TILE;
   static constexpr int A_BYTES = TILE_M * KC;
   static constexpr int B_BYTES = N_TILE * KC;
@@ -63,7 +67,7 @@ struct TcCfg {
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
   static_assert(!B_RESIDENT || N_TILES == 1, "resident weights need a single N tile");
   static_assert(!CONV || ROWS * NB * IMG == TILE_M, "tile geometry");
-  static_assert(!POOL || (CONV && ROWS % 2 == 0 && N_TILES == 1), "pool fusion needs whole 2x2 windows in a tile");
+  static_assert(!POOL || (CONV && ROWS % 2 == 0), "pool fusion needs whole 2x2 windows in a tile");
 };
 
 struct TcArgs {
@@ -85,11 +89,11 @@ __device__ __forceinline__ int staging_off(int p, int j) {
   return p * N + ((j ^ f) << 4);
 }
 
-template <int IMG, int CIN, int COUT, bool B_RESIDENT, bool POOL, bool CHECK>
+template <int IMG, int CIN, int COUT, bool B_RESIDENT, bool POOL, bool CHECK, int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const TcArgs args) {
-  using C = TcCfg<IMG, CIN, COUT, B_RESIDENT, POOL>;
+  using C = TcCfg<IMG, CIN, COUT, B_RESIDENT, POOL, NT>;
   extern __shared__ uint8_t smem_raw[];
   // 1 KiB alignment for the 128B-swizzle atoms; plain pointer arithmetic keeps the shared address space visible to
   // the compiler (LDS/STS instead of generic loads)
@@ -316,7 +320,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           o.w = max4_u8x4(a.w, b.w, c.w, d.w);
           const int64_t img = img_base + nb;
           if (img < args.m_rows) {
-            uint8_t* dst = args.y + ((img * (IMG / 2) + prow0 + pr) * (int64_t)PW + pw) * COUT + j * 16;
+            uint8_t* dst = args.y + ((img * (IMG / 2) + prow0 + pr) * (int64_t)PW + pw) * COUT +
+                           (tile % C::N_TILES) * C::N_TILE + j * 16;
             *reinterpret_cast<uint4*>(dst) = o;
           }
         }
@@ -334,10 +339,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 }
 
 // --------------------------------------------------------------------------------------------------------- host side
-template <int IMG, int CIN, int COUT, bool B_RESIDENT, bool POOL, bool CHECK = true>
+template <int IMG, int CIN, int COUT, bool B_RESIDENT, bool POOL, bool CHECK = true, int NT = 0>
 static int launch_tc(const uint8_t* x, uint8_t* y, int64_t m_rows, const int8_t* w, const int32_t* corr,
                      const b200q_requant& rq, cudaStream_t stream) {
-  using C = TcCfg<IMG, CIN, COUT, B_RESIDENT, POOL>;
+  using C = TcCfg<IMG, CIN, COUT, B_RESIDENT, POOL, NT>;
   CUtensorMap map_a, map_b;
   int num_m_tiles;
   int rc;
@@ -366,9 +371,9 @@ static int launch_tc(const uint8_t* x, uint8_t* y, int64_t m_rows, const int8_t*
   }
   if constexpr (CHECK && COUT == 64) {  // epilogue-critical layers: drop the per-element range test when it is provably idle
     if ((rq.flags & B200Q_RQ_BOUNDED) && (rq.flags & B200Q_RQ_ACC22))
-      return launch_tc<IMG, CIN, COUT, B_RESIDENT, POOL, false>(x, y, m_rows, w, corr, rq, stream);
+      return launch_tc<IMG, CIN, COUT, B_RESIDENT, POOL, false, NT>(x, y, m_rows, w, corr, rq, stream);
   }
-  auto kernel = igemm_tc_kernel<IMG, CIN, COUT, B_RESIDENT, POOL, CHECK>;
+  auto kernel = igemm_tc_kernel<IMG, CIN, COUT, B_RESIDENT, POOL, CHECK, NT>;
   static uint64_t attr_mask = 0;  // per template instantiation
   if (int arc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), C::SMEM_BYTES, &attr_mask)) return arc;
   TcArgs args{y, rq.mult, rq.bdiv, corr, m_rows, num_m_tiles, rq.zp_out, rq.relu ? rq.zp_out : 0,
@@ -391,6 +396,19 @@ static bool force_streamed() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200Q_TC_STREAM_WEIGHTS");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// -DB200Q_DEV builds only: B200Q_NO_SMALL=1 disables the small-batch kernel selection (A-B timing only).
+static bool small_batch_off() {
+#ifndef B200Q_DEV
+  return false;
+#endif
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200Q_NO_SMALL");
     v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
@@ -419,6 +437,25 @@ extern "C" int b200q_conv3x3_tc(const uint8_t* x, uint8_t* y, int64_t b, const b
   cudaStream_t s = (cudaStream_t)stream;
   const bool streamed = force_streamed();
   const bool pool = pool2x2 != 0;
+  // Small batches (the latency-bound regime the whole-network executor serves): the band-resident kernels below give a
+  // whole image (or four) to ONE CTA, so at batch 1 a layer is a serial walk over its tiles on one SM.  When the layer
+  // cut into 128-pixel x 64-channel tiles still fits in about two waves of CTAs, it runs as that many independent CTAs
+  // instead (shifted-TMA kernel, N tile 64, streamed weights).  Same arithmetic, bit-identical results.
+  {
+    const int64_t m_tiles = L->img == 32 ? b * 8 : L->img == 16 ? b * 2 : (b + 1) / 2;
+    const bool small = !small_batch_off() && m_tiles * (L->cout / 64) <= 2 * (int64_t)num_sms();
+#define B200Q_SMALL_CASE(IMG_, CIN_, COUT_)                                                                       \
+  if (small && L->img == IMG_ && L->cin == CIN_ && L->cout == COUT_) {                                            \
+    if (pool) return launch_tc<IMG_, CIN_, COUT_, false, true, true, 64>(x, y, b, L->w, L->corr, L->rq, s);       \
+    return launch_tc<IMG_, CIN_, COUT_, false, false, true, 64>(x, y, b, L->w, L->corr, L->rq, s);                \
+  }
+    B200Q_SMALL_CASE(32, 64, 64)
+    B200Q_SMALL_CASE(16, 64, 128)
+    B200Q_SMALL_CASE(16, 128, 128)
+    B200Q_SMALL_CASE(8, 128, 256)
+    B200Q_SMALL_CASE(8, 256, 256)
+#undef B200Q_SMALL_CASE
+  }
   if (!no_halo()) {
     int rc = 0;
     if (conv3x3_halo_dispatch(x, y, b, L, pool, s, &rc) == 0) return rc;
@@ -450,8 +487,13 @@ extern "C" int b200q_linear_tc(const uint8_t* x, uint8_t* y, int64_t b, const b2
                 "linear_tc: buffers must be 16-byte aligned");
   if (b == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (L->k == 4096 && L->n == 512)
+  if (L->k == 4096 && L->n == 512) {
+    // few rows: eight 64-column CTA tiles per 128 rows instead of two 256-column ones (each CTA then streams 256 KB of
+    // the 2 MB weight matrix instead of 1 MB)
+    if (!small_batch_off() && (b + TILE_M - 1) / TILE_M * 8 <= (int64_t)num_sms())
+      return launch_tc<0, 4096, 512, false, false, true, 64>(x, y, b, L->w, L->corr, L->rq, s);
     return launch_tc<0, 4096, 512, false, false>(x, y, b, L->w, L->corr, L->rq, s);
+  }
   if (L->k == 512 && L->n == 64) return launch_tc<0, 512, 64, false, false>(x, y, b, L->w, L->corr, L->rq, s);
   set_error("linear_tc: unsupported geometry k=%d n=%d", L->k, L->n);
   return B200Q_ERR_INVALID_ARG;

@@ -8,8 +8,55 @@ computes in one process.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
+
+
+def parse_cpulist(text: str) -> set[int]:
+    """``"0-3,8,10-11"`` (sysfs ``local_cpulist`` syntax) -> ``{0,1,2,3,8,10,11}``."""
+    cpus: set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_info(device_index: int) -> dict:
+    """NUMA node and local CPUs of a GPU as the kernel reports them (``/sys/bus/pci/devices/<bdf>/``)."""
+    info = {"pci_bus_id": None, "numa_node": None, "local_cpus": None}
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        info["pci_bus_id"] = bdf
+        base = f"/sys/bus/pci/devices/{bdf}"
+        with open(f"{base}/numa_node") as f:
+            info["numa_node"] = int(f.read().strip())
+        with open(f"{base}/local_cpulist") as f:
+            info["local_cpus"] = sorted(parse_cpulist(f.read()))
+    except (OSError, AttributeError, ValueError, RuntimeError):
+        pass
+    return info
+
+
+def bind_to_gpu_numa(device_index: int) -> dict:
+    """Pin the calling process to the CPUs that are local to ``device_index`` (when the container's CPU set contains
+    any), BEFORE it allocates pinned host buffers: page placement follows the allocating thread, and a rank whose
+    staging buffers sit on the other socket pays a UPI hop on every host->device copy.  One process per GPU, so this
+    is per rank.  Returns what was found and what was done (bench.py reports it)."""
+    info = gpu_numa_info(device_index)
+    allowed = os.sched_getaffinity(0)
+    info["allowed_cpus"] = len(allowed)
+    info["bound_cpus"] = None
+    local = set(info["local_cpus"] or ()) & allowed
+    if local and local != allowed:
+        os.sched_setaffinity(0, local)
+        info["bound_cpus"] = len(local)
+    info["local_cpus"] = len(info["local_cpus"]) if info["local_cpus"] is not None else None
+    return info
 
 
 def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:

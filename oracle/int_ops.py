@@ -144,11 +144,15 @@ def dynamic_qparams(mn: float, mx: float, qmin: int = 0, qmax: int = 127):
 
 def linear_dynamic(x_f32: np.ndarray, w_int8: np.ndarray, w_scale: float, bias: np.ndarray) -> np.ndarray:
     """quantized::linear_dynamic(x, W, reduce_range=True): fp32 [B,K] -> fp32 [B,N].
-    Per-tensor min/max over the WHOLE input; weights per-tensor symmetric qint8."""
+    Per-tensor min/max over the WHOLE input; weights per-tensor symmetric qint8.  Activations are quantised the way
+    fbgemm's PackAWithQuantRowOffset does it: the zero-point is added in fp32 before the rounding, as one fused
+    multiply-add, ``q = clamp(rne(fma(x, 1/s, zp)), 0, 255)`` (the float64 product of two binary32 numbers is exact, so
+    rounding the float64 sum to binary32 IS the single rounding of an fma).  tests/test_oracle.py pins this form
+    against the live op (``rne(x/s)+zp`` differs on ~3 elements per million)."""
     x = x_f32.astype(F32)
     s_x, zp = dynamic_qparams(x.min(), x.max())
     inv = F32(1.0) / s_x
-    xq = np.clip(np.rint(x * inv).astype(np.int64) + zp, 0, 255)
+    xq = np.clip(np.rint((x.astype(np.float64) * np.float64(inv) + np.float64(zp)).astype(F32)).astype(np.int64), 0, 255)
     acc = ((xq - zp).astype(np.float64) @ w_int8.astype(np.float64).T)
     return (acc.astype(F32) * F32(s_x * F32(w_scale)) + bias.astype(F32)).astype(F32)
 

@@ -155,9 +155,11 @@ def _stress_layer(name, qparams, huge):
 @pytest.mark.parametrize("name", ["conv2", "conv3", "conv6"])
 @pytest.mark.parametrize("mode", ["huge_acc", "big_mult"])
 @pytest.mark.parametrize("pool", [False, True])
-def test_conv_tc_requant_fallback_paths(qparams, name, mode, pool):
+@pytest.mark.parametrize("b", [2, 160])
+def test_conv_tc_requant_fallback_paths(qparams, name, mode, pool, b):
     """The conversion-free epilogue must hand over to the exact I2F/F2I form (run-time range test, or the BOUNDED flag
-    withheld at pack time) and stay bit-exact: accumulators up to ~7e7 and multipliers > 0.5."""
+    withheld at pack time) and stay bit-exact: accumulators up to ~7e7 and multipliers > 0.5.  b = 2 runs the small-batch
+    kernel (shifted TMA, N tile 64), b = 160 the band-resident kernels (conv_halo.cu / conv_pair.cu)."""
     from convnet_quantization_b200 import _lib, ops
     from convnet_quantization_b200.packing import PackedConv
     from tests.conftest import qparams_to_numpy
@@ -178,7 +180,7 @@ def test_conv_tc_requant_fallback_paths(qparams, name, mode, pool):
     else:
         assert not (pc.c.rq.flags & _lib.RQ_ACC22)
     g = torch.Generator().manual_seed(3)
-    x = torch.randint(0, 256, (2, pc.img, pc.img, pc.cin), generator=g, dtype=torch.uint8)
+    x = torch.randint(0, 256, (b, pc.img, pc.img, pc.cin), generator=g, dtype=torch.uint8)
     x[0] = 255   # one saturated image: every accumulator of it is at the extreme
     x[1, : pc.img // 2] = 0
     Lnp = qparams_to_numpy({"l": L})["l"]

@@ -148,3 +148,32 @@ def test_sandwich_golden_from_reference_classes(fp32_net):
             a = a.transpose(0, 2, 3, 1)
         assert hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() == str(g[f"sandwich_{n}_sha"]), n
     np.testing.assert_allclose(logits.numpy(), g["sandwich_logits"], rtol=1e-5, atol=1e-5)
+
+
+def test_dynamic_activation_quantisation_is_a_fused_multiply_add():
+    """Which rounding does fbgemm use for the activations of quantized::linear_dynamic?  An identity-like weight matrix
+    exposes every quantised activation in the output; over 2 M elements the fma form must reproduce ALL of them."""
+    torch.backends.quantized.engine = "fbgemm"
+    k = 256
+    lin = torch.nn.Linear(k, k, bias=False)
+    with torch.no_grad():
+        lin.weight.copy_(torch.eye(k))
+    qlin = torch.ao.quantization.quantize_dynamic(torch.nn.Sequential(lin), {torch.nn.Linear}, dtype=torch.qint8)[0]
+    w = qlin.weight()
+    assert int(w.int_repr().diagonal().min()) == 127
+    g = torch.Generator().manual_seed(0)
+    mism = {"fma": 0, "mul_then_add_int": 0}
+    for it in range(4):
+        x = torch.randn(2048, k, generator=g) * (0.3 + 0.4 * it) + 0.3 * it
+        y = qlin(x).numpy()
+        xn = x.numpy()
+        s_x, zp = IO.dynamic_qparams(xn.min(), xn.max())
+        inv = np.float32(1.0) / s_x
+        xq = np.rint(y.astype(np.float64) / (np.float64(np.float32(s_x * np.float32(w.q_scale()))) * 127)).astype(np.int64) + zp
+        fma = np.clip(np.rint((xn.astype(np.float64) * np.float64(inv) + zp).astype(np.float32)).astype(np.int64), 0, 255)
+        mul = np.clip(np.rint(xn * inv).astype(np.int64) + zp, 0, 255)
+        mism["fma"] += int((fma != xq).sum())
+        mism["mul_then_add_int"] += int((mul != xq).sum())
+        got = IO.linear_dynamic(xn, w.int_repr().numpy(), w.q_scale(), np.zeros(k, np.float32))
+        np.testing.assert_allclose(got, y, rtol=1e-6, atol=1e-6 * np.abs(y).max())
+    assert mism["fma"] == 0 and mism["mul_then_add_int"] > 0, mism

@@ -52,3 +52,11 @@ def test_sharded_accuracy_matches_single_process():
     labels = torch.randint(0, 10, (n,), generator=torch.Generator().manual_seed(5))
     want = sharding.sharded_accuracy(net, images, labels, 0, 1, batch=64)
     assert got[0] == got[1] == want and want[2] == n
+
+
+def test_cpulist_parsing_and_numa_binding_are_safe_without_a_gpu():
+    from convnet_quantization_b200 import sharding
+    assert sharding.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert sharding.parse_cpulist("") == set()
+    info = sharding.bind_to_gpu_numa(0)  # no GPU / no sysfs entry: reports, changes nothing
+    assert info["allowed_cpus"] >= 1 and info["bound_cpus"] in (None, info["bound_cpus"])
