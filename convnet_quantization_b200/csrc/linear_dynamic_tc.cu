@@ -12,15 +12,17 @@
 // columns (n = 512: two N=256 accumulators = the whole TMEM), so x is quantised once per row block; the weights are
 // re-streamed per row block from L2 (2 MB for fc1; 64-byte K chunks, 5 stages in flight).
 //
-// Warp roles (448 threads): warps 0..3 epilogue (warp q may only read TMEM lanes 32q..32q+31), warps 4..11 producers,
-// warp 12 TMA (weights), warp 13 MMA issuer + TMEM owner.
+// Warp roles (704 threads): warps 0..3 epilogue (warp q may only read TMEM lanes 32q..32q+31), warps 4..19 producers,
+// warp 20 TMA (weights), warp 21 MMA issuer + TMEM owner.  The producers are what keeps HBM busy: each keeps the loads
+// of THREE K chunks in flight while it quantises a fourth (a ring of four register buffers; 96 KB in flight per SM -
+// with one chunk of look-ahead the kernel ran at 2.85 TB/s, r02 ncu).
 #include "common.cuh"
 
 namespace b200q {
 
 int launch_minmax(const float* x, int64_t n, float* out5, void* scratch, cudaStream_t s, bool dynamic);
 
-constexpr int LD_EPI_WARPS = 4, LD_PROD_WARPS = 8;
+constexpr int LD_EPI_WARPS = 4, LD_PROD_WARPS = 16;
 constexpr int LD_PROD_WARP0 = LD_EPI_WARPS;
 constexpr int LD_TMA_WARP = LD_EPI_WARPS + LD_PROD_WARPS, LD_MMA_WARP = LD_TMA_WARP + 1;
 constexpr int LD_THREADS = 32 * (LD_MMA_WARP + 1);
@@ -95,18 +97,19 @@ linear_dynamic_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LdArgs
 
   if (warp >= LD_PROD_WARP0 && warp < LD_TMA_WARP) {
     // ================================================================== producers: fp32 rows -> u8 SW64 tiles
-    // A warp-wide 16-byte load covers two rows of the chunk (2 x 64 floats); warp pw owns rows 16*pw .. 16*pw+15, thread
-    // (lane) holds floats 4*(lane&15)..+3 of rows 16*pw + 2*i + (lane>>4), i = 0..7.  The loads of chunk kc+1 are in
-    // flight while chunk kc is quantised (two register buffers, loop unrolled by two).
+    // A warp-wide 16-byte load covers two rows of the chunk (2 x 64 floats); warp pw owns rows 8*pw .. 8*pw+7, thread
+    // (lane) holds floats 4*(lane&15)..+3 of rows 8*pw + 2*i + (lane>>4), i = 0..3.
     const int pw = warp - LD_PROD_WARP0;
     const float inv_scale = __ldg(args.qp + 3);
     const float zp_f = __ldg(args.qp + 4);
     const int col4 = lane & 15, rsub = lane >> 4;
-    float4 buf0[8], buf1[8];
-    auto load = [&](float4 (&v)[8], int64_t m0, int kc) {
+    constexpr int RPT = 4;   // rows (16-byte loads) per thread and chunk
+    constexpr int RING = 4;  // register buffers: RING - 1 chunks of look-ahead
+    float4 buf[RING][RPT];
+    auto load = [&](float4 (&v)[RPT], int64_t m0, int kc) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int64_t row = m0 + 16 * pw + 2 * i + rsub;
+      for (int i = 0; i < RPT; ++i) {
+        int64_t row = m0 + 2 * RPT * pw + 2 * i + rsub;
         row = row < args.b ? row : args.b - 1;  // rows past the batch: re-read the last row (never stored)
         v[i] = __ldg(reinterpret_cast<const float4*>(args.x + row * args.k + kc * LD_KC) + col4);
       }
@@ -126,12 +129,12 @@ linear_dynamic_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LdArgs
       return pack_sat_u8(q1, q0, pack_sat_u8(q3, q2, 0u));
     };
     uint32_t stage = 0, phase = 0;
-    auto emit = [&](const float4 (&v)[8]) {
+    auto emit = [&](const float4 (&v)[RPT]) {
       mbar_wait(empty_bar + stage, phase ^ 1);
       uint8_t* a_st = a_smem + stage * C::A_BYTES;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = 16 * pw + 2 * i + rsub;
+      for (int i = 0; i < RPT; ++i) {
+        const int r = 2 * RPT * pw + 2 * i + rsub;
         // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9) = (row >> 1) & 3
         const int off = r * LD_KC + ((((col4 >> 2) ^ ((r >> 1) & 3))) << 4) + (col4 & 3) * 4;
         *reinterpret_cast<uint32_t*>(a_st + off) = quant4(v[i]);
@@ -146,12 +149,17 @@ linear_dynamic_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LdArgs
     };
     for (int tile = blockIdx.x; tile < args.num_m_tiles; tile += gridDim.x) {
       const int64_t m0 = (int64_t)tile * LD_M;
-      load(buf0, m0, 0);
-      for (int kc = 0; kc < nk; kc += 2) {  // nk is even (k % 128 == 0)
-        load(buf1, m0, kc + 1);
-        emit(buf0);
-        if (kc + 2 < nk) load(buf0, m0, kc + 2);
-        emit(buf1);
+#pragma unroll
+      for (int d = 0; d < RING - 1; ++d)
+        if (d < nk) load(buf[d], m0, d);
+      for (int kc = 0; kc < nk; kc += RING) {  // unrolled by RING so that the buffer indices are compile-time
+#pragma unroll
+        for (int j = 0; j < RING; ++j) {
+          if (kc + j < nk) {
+            if (kc + j + RING - 1 < nk) load(buf[(j + RING - 1) % RING], m0, kc + j + RING - 1);
+            emit(buf[j]);
+          }
+        }
       }
     }
   } else if (warp == LD_TMA_WARP) {
@@ -240,24 +248,27 @@ linear_dynamic_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LdArgs
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty_bar);
         }
-        float o[CW];
+        float* dst = args.y + row * args.n + c0;
+        const bool vec = args.n % 4 == 0 && c0 + CW <= args.n;
 #pragma unroll
-        for (int j = 0; j < CW; ++j) {
-          const int nn = c0 + j;
-          const int nc = nn < args.n ? nn : args.n - 1;  // padded columns (n < NT): computed, never stored
-          const int t = (int)v[j] - zp * __ldg(args.wsum + nc);
-          float r = __fadd_rn(__fmul_rn(__int2float_rn(t), s_xw), __ldg(args.bias + nc));
-          o[j] = args.relu ? fmaxf(r, 0.0f) : r;
-        }
-        if (valid) {
-          float* dst = args.y + row * args.n + c0;
-          if (args.n % 4 == 0 && c0 + CW <= args.n) {
+        for (int j0 = 0; j0 < CW; j0 += 4) {  // four columns at a time: keeps the live set small (704 threads per CTA)
+          float o[4];
 #pragma unroll
-            for (int j = 0; j < CW; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-          } else {
+          for (int j = 0; j < 4; ++j) {
+            const int nn = c0 + j0 + j;
+            const int nc = nn < args.n ? nn : args.n - 1;  // padded columns (n < NT): computed, never stored
+            const int t = (int)v[j0 + j] - zp * __ldg(args.wsum + nc);
+            const float r = __fadd_rn(__fmul_rn(__int2float_rn(t), s_xw), __ldg(args.bias + nc));
+            o[j] = args.relu ? fmaxf(r, 0.0f) : r;
+          }
+          if (valid) {
+            if (vec) {
+              *reinterpret_cast<float4*>(dst + j0) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < CW; ++j)
-              if (c0 + j < args.n) dst[j] = o[j];
+              for (int j = 0; j < 4; ++j)
+                if (c0 + j0 + j < args.n) dst[j0 + j] = o[j];
+            }
           }
         }
       }
@@ -300,8 +311,8 @@ extern "C" int b200q_linear_dynamic(const float* x, float* y, int64_t b, int k, 
   B200Q_REQUIRE(x && y && w && wsum && bias && scratch, "linear_dynamic: null pointer");
   B200Q_REQUIRE(scratch_bytes >= B200Q_REDUCE_SCRATCH_BYTES, "linear_dynamic: scratch too small (%lld < %d)",
                 (long long)scratch_bytes, B200Q_REDUCE_SCRATCH_BYTES);
-  B200Q_REQUIRE(k > 0 && k % 128 == 0 && (n == 512 || (n > 0 && n <= 16)),
-                "linear_dynamic: unsupported shape k=%d n=%d (need k %% 128 == 0 and n == 512 or n <= 16)", k, n);
+  B200Q_REQUIRE(k > 0 && k % 64 == 0 && (n == 512 || (n > 0 && n <= 16)),
+                "linear_dynamic: unsupported shape k=%d n=%d (need k %% 64 == 0 and n == 512 or n <= 16)", k, n);
   B200Q_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 && (uintptr_t)w % 16 == 0 && (uintptr_t)scratch % 16 == 0,
                 "linear_dynamic: buffers must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
