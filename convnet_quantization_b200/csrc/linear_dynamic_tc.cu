@@ -10,19 +10,22 @@
 // The quantised activations never exist in HBM: the layer reads its fp32 input exactly twice (min/max pass + this
 // kernel) and is bound by that stream (fc1: 16 KB per image against 4.2 MOP).  A CTA owns 128 rows and ALL n output
 // columns (n = 512: two N=256 accumulators = the whole TMEM), so x is quantised once per row block; the weights are
-// re-streamed per row block from L2 (2 MB for fc1; 64-byte K chunks, 5 stages in flight).
+// re-streamed per row block from L2 (2 MB for fc1; 64-byte K chunks).
 //
-// Warp roles (704 threads): warps 0..3 epilogue (warp q may only read TMEM lanes 32q..32q+31), warps 4..19 producers,
-// warp 20 TMA (weights), warp 21 MMA issuer + TMEM owner.  The producers are what keeps HBM busy: each keeps the loads
-// of THREE K chunks in flight while it quantises a fourth (a ring of four register buffers; 96 KB in flight per SM -
-// with one chunk of look-ahead the kernel ran at 2.85 TB/s, r02 ncu).
+// The fp32 rows are staged by TMA: a [128 rows][64 floats] box (32 KB) per K chunk into a three-deep shared-memory ring,
+// i.e. 96 KB of HBM reads in flight per SM without a single register (the first version loaded through registers with one
+// chunk of look-ahead and ran at 2.85 TB/s: every chunk exposed an HBM round trip; a deeper register ring was slower
+// still - ptxas folded the in-flight loads onto shared scoreboards).  Rows past the batch are zero-filled by TMA.
+//
+// Warp roles (448 threads): warps 0..3 epilogue (warp q may only read TMEM lanes 32q..32q+31), warps 4..11 producers
+// (shared fp32 -> shared u8), warp 12 TMA (fp32 rows and weights), warp 13 MMA issuer + TMEM owner.
 #include "common.cuh"
 
 namespace b200q {
 
 int launch_minmax(const float* x, int64_t n, float* out5, void* scratch, cudaStream_t s, bool dynamic);
 
-constexpr int LD_EPI_WARPS = 4, LD_PROD_WARPS = 16;
+constexpr int LD_EPI_WARPS = 4, LD_PROD_WARPS = 8;
 constexpr int LD_PROD_WARP0 = LD_EPI_WARPS;
 constexpr int LD_TMA_WARP = LD_EPI_WARPS + LD_PROD_WARPS, LD_MMA_WARP = LD_TMA_WARP + 1;
 constexpr int LD_THREADS = 32 * (LD_MMA_WARP + 1);
@@ -34,10 +37,12 @@ struct LdCfg {
   static constexpr int MMA_N = NT > 256 ? 256 : NT;
   static constexpr int N_MMAS = NT / MMA_N;
   static constexpr int A_BYTES = LD_M * LD_KC, B_BYTES = NT * LD_KC;
+  static constexpr int RAW_BYTES = LD_M * LD_KC * 4;  // one K chunk of fp32 rows
+  static constexpr int RAW_STAGES = 3;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+  static constexpr int STAGES_FIT = (216 * 1024 - RAW_STAGES * RAW_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
+  static constexpr int SMEM_BYTES = RAW_STAGES * RAW_BYTES + STAGES * STAGE_BYTES + 256 + 1024;
   static constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
   static_assert(NT % MMA_N == 0 && MMA_N % 16 == 0 && MMA_N >= 16, "N tile");
   static_assert(B_BYTES % 1024 == 0, "stage alignment");
@@ -60,15 +65,19 @@ struct LdArgs {
 
 template <int NT>
 __global__ void __launch_bounds__(LD_THREADS, 1)
-linear_dynamic_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LdArgs args) {
+linear_dynamic_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                         const LdArgs args) {
   using C = LdCfg<NT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_smem = smem;                                   // [STAGES][128][64 B]
   uint8_t* b_smem = a_smem + C::STAGES * C::A_BYTES;        // [STAGES][NT][64 B]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(b_smem + C::STAGES * C::B_BYTES);
+  uint8_t* x_smem = b_smem + C::STAGES * C::B_BYTES;        // [RAW_STAGES][128][64 floats]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(x_smem + C::RAW_STAGES * C::RAW_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
+  uint64_t* raw_full_bar = empty_bar + C::STAGES;           // [RAW_STAGES] fp32 chunk landed (TMA)
+  uint64_t* raw_empty_bar = raw_full_bar + C::RAW_STAGES;   // [RAW_STAGES] fp32 chunk converted by all producer warps
+  uint64_t* tmem_full_bar = raw_empty_bar + C::RAW_STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 1;
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
 
@@ -77,10 +86,15 @@ linear_dynamic_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LdArgs
   const int nk = args.k / LD_KC;
 
   if (warp == LD_TMA_WARP && lane == 0) {
+    tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(full_bar + i, LD_PROD_WARPS + 1);  // one arrive per producer warp + the TMA thread's arrive.expect_tx
       mbar_init(empty_bar + i, 1);
+    }
+    for (int i = 0; i < C::RAW_STAGES; ++i) {
+      mbar_init(raw_full_bar + i, 1);
+      mbar_init(raw_empty_bar + i, LD_PROD_WARPS);
     }
     mbar_init(tmem_full_bar, 1);
     mbar_init(tmem_empty_bar, LD_EPI_WARPS);
@@ -96,24 +110,13 @@ linear_dynamic_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LdArgs
   const uint32_t tmem_base = *tmem_base_smem;
 
   if (warp >= LD_PROD_WARP0 && warp < LD_TMA_WARP) {
-    // ================================================================== producers: fp32 rows -> u8 SW64 tiles
-    // A warp-wide 16-byte load covers two rows of the chunk (2 x 64 floats); warp pw owns rows 8*pw .. 8*pw+7, thread
-    // (lane) holds floats 4*(lane&15)..+3 of rows 8*pw + 2*i + (lane>>4), i = 0..3.
+    // ================================================================== producers: shared fp32 rows -> u8 SW64 tiles
+    // A warp-wide 16-byte shared load covers two rows of the chunk (2 x 64 floats, 512 contiguous bytes: conflict-free);
+    // warp pw owns rows 16*pw .. 16*pw+15, thread (lane) converts floats 4*(lane&15)..+3 of rows 16*pw + 2*i + (lane>>4).
     const int pw = warp - LD_PROD_WARP0;
     const float inv_scale = __ldg(args.qp + 3);
     const float zp_f = __ldg(args.qp + 4);
     const int col4 = lane & 15, rsub = lane >> 4;
-    constexpr int RPT = 4;   // rows (16-byte loads) per thread and chunk
-    constexpr int RING = 4;  // register buffers: RING - 1 chunks of look-ahead
-    float4 buf[RING][RPT];
-    auto load = [&](float4 (&v)[RPT], int64_t m0, int kc) {
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        int64_t row = m0 + 2 * RPT * pw + 2 * i + rsub;
-        row = row < args.b ? row : args.b - 1;  // rows past the batch: re-read the last row (never stored)
-        v[i] = __ldg(reinterpret_cast<const float4*>(args.x + row * args.k + kc * LD_KC) + col4);
-      }
-    };
     // fbgemm quantises the activations of a dynamic linear with the zero-point added in fp32 BEFORE the rounding to
     // integer, as ONE fused multiply-add: q = clamp(rne(fma(x, 1/s, zp)), 0, 255) (PackAWithQuantRowOffset; found by
     // experiment - 0 mismatches over 4.2e7 elements against quantized::linear_dynamic, while rne(x/s)+zp misses 134 and
@@ -128,46 +131,52 @@ linear_dynamic_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LdArgs
       const int q3 = __float_as_int(__fadd_rn(__fmaf_rn(v.w, inv_scale, zp_f), MAGIC_F)) + UNMAGIC;
       return pack_sat_u8(q1, q0, pack_sat_u8(q3, q2, 0u));
     };
-    uint32_t stage = 0, phase = 0;
-    auto emit = [&](const float4 (&v)[RPT]) {
-      mbar_wait(empty_bar + stage, phase ^ 1);
-      uint8_t* a_st = a_smem + stage * C::A_BYTES;
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        const int r = 2 * RPT * pw + 2 * i + rsub;
-        // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9) = (row >> 1) & 3
-        const int off = r * LD_KC + ((((col4 >> 2) ^ ((r >> 1) & 3))) << 4) + (col4 & 3) * 4;
-        *reinterpret_cast<uint32_t*>(a_st + off) = quant4(v[i]);
-      }
-      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar + stage);
-      if (++stage == C::STAGES) {
-        stage = 0;
-        phase ^= 1;
-      }
-    };
+    uint32_t stage = 0, phase = 0, rstage = 0, rphase = 0;
     for (int tile = blockIdx.x; tile < args.num_m_tiles; tile += gridDim.x) {
-      const int64_t m0 = (int64_t)tile * LD_M;
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(raw_full_bar + rstage, rphase);
+        const float4* src = reinterpret_cast<const float4*>(x_smem + rstage * C::RAW_BYTES);
+        float4 v[8];
 #pragma unroll
-      for (int d = 0; d < RING - 1; ++d)
-        if (d < nk) load(buf[d], m0, d);
-      for (int kc = 0; kc < nk; kc += RING) {  // unrolled by RING so that the buffer indices are compile-time
+        for (int i = 0; i < 8; ++i) v[i] = src[(16 * pw + 2 * i + rsub) * (LD_KC / 4) + col4];
+        mbar_wait(empty_bar + stage, phase ^ 1);
+        uint8_t* a_st = a_smem + stage * C::A_BYTES;
 #pragma unroll
-        for (int j = 0; j < RING; ++j) {
-          if (kc + j < nk) {
-            if (kc + j + RING - 1 < nk) load(buf[(j + RING - 1) % RING], m0, kc + j + RING - 1);
-            emit(buf[j]);
-          }
+        for (int i = 0; i < 8; ++i) {
+          const int r = 16 * pw + 2 * i + rsub;
+          // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9) = (row >> 1) & 3
+          const int off = r * LD_KC + ((((col4 >> 2) ^ ((r >> 1) & 3))) << 4) + (col4 & 3) * 4;
+          *reinterpret_cast<uint32_t*>(a_st + off) = quant4(v[i]);
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(raw_empty_bar + rstage);  // this warp's rows of the fp32 chunk are consumed
+          mbar_arrive(full_bar + stage);
+        }
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (++rstage == C::RAW_STAGES) {
+          rstage = 0;
+          rphase ^= 1;
         }
       }
     }
   } else if (warp == LD_TMA_WARP) {
-    // ================================================================== weights by TMA
+    // ================================================================== fp32 rows and weights by TMA
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, rstage = 0, rphase = 0;
       for (int tile = blockIdx.x; tile < args.num_m_tiles; tile += gridDim.x) {
         for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(raw_empty_bar + rstage, rphase ^ 1);
+          mbar_expect_tx(raw_full_bar + rstage, C::RAW_BYTES);  // rows past the batch are zero-filled, still counted
+          tma_load_2d(x_smem + rstage * C::RAW_BYTES, &map_x, raw_full_bar + rstage, kc * LD_KC * 4, tile * LD_M);
+          if (++rstage == C::RAW_STAGES) {
+            rstage = 0;
+            rphase ^= 1;
+          }
           mbar_wait(empty_bar + stage, phase ^ 1);
           mbar_expect_tx(full_bar + stage, C::B_BYTES);
           uint8_t* b_st = b_smem + stage * C::B_BYTES;
@@ -248,27 +257,27 @@ linear_dynamic_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LdArgs
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty_bar);
         }
-        float* dst = args.y + row * args.n + c0;
-        const bool vec = args.n % 4 == 0 && c0 + CW <= args.n;
+        float o[CW];
 #pragma unroll
-        for (int j0 = 0; j0 < CW; j0 += 4) {  // four columns at a time: keeps the live set small (704 threads per CTA)
-          float o[4];
+        for (int j = 0; j < CW; ++j) {
+          const int nn = c0 + j;
+          const int nc = nn < args.n ? nn : args.n - 1;  // padded columns (n < NT): computed, never stored
+          const int t = (int)v[j] - zp * __ldg(args.wsum + nc);
+          // fbgemm's output stage is ONE fused multiply-add, fma(f32(acc), s_x*s_w, bias), with the scale product rounded
+          // to fp32 first (found by experiment: bit-identical to quantized::linear_dynamic on every element tried,
+          // tests/test_oracle.py; separately rounded mul + add differs in the last place on ~25 % of them)
+          float r = __fmaf_rn(__int2float_rn(t), s_xw, __ldg(args.bias + nc));
+          o[j] = args.relu ? fmaxf(r, 0.0f) : r;
+        }
+        if (valid) {
+          float* dst = args.y + row * args.n + c0;
+          if (args.n % 4 == 0 && c0 + CW <= args.n) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int nn = c0 + j0 + j;
-            const int nc = nn < args.n ? nn : args.n - 1;  // padded columns (n < NT): computed, never stored
-            const int t = (int)v[j0 + j] - zp * __ldg(args.wsum + nc);
-            const float r = __fadd_rn(__fmul_rn(__int2float_rn(t), s_xw), __ldg(args.bias + nc));
-            o[j] = args.relu ? fmaxf(r, 0.0f) : r;
-          }
-          if (valid) {
-            if (vec) {
-              *reinterpret_cast<float4*>(dst + j0) = make_float4(o[0], o[1], o[2], o[3]);
-            } else {
+            for (int j = 0; j < CW; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+          } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (c0 + j0 + j < args.n) dst[j0 + j] = o[j];
-            }
+            for (int j = 0; j < CW; ++j)
+              if (c0 + j < args.n) dst[j] = o[j];
           }
         }
       }
@@ -286,7 +295,13 @@ linear_dynamic_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LdArgs
 template <int NT>
 static int launch_linear_dynamic(const LdArgs& a, const int8_t* w, cudaStream_t s) {
   using C = LdCfg<NT>;
-  CUtensorMap map_w;
+  CUtensorMap map_x, map_w;
+  {  // fp32 rows as bytes: [b][4k] uint8, box = 256 bytes (64 floats) x 128 rows, no swizzle
+    const uint64_t xdims[2] = {(uint64_t)a.k * 4, (uint64_t)a.b};
+    const uint64_t xstrides[1] = {(uint64_t)a.k * 4};
+    const uint32_t xbox[2] = {(uint32_t)LD_KC * 4, (uint32_t)LD_M};
+    if (int rc = encode_tensor_map(&map_x, a.x, 2, xdims, xstrides, xbox, 0)) return rc;
+  }
   const uint64_t dims[2] = {(uint64_t)a.k, (uint64_t)a.n};
   const uint64_t strides[1] = {(uint64_t)a.k};
   const uint32_t box[2] = {(uint32_t)LD_KC, (uint32_t)C::MMA_N};  // rows >= n (n < NT) are zero-filled by TMA
@@ -295,7 +310,7 @@ static int launch_linear_dynamic(const LdArgs& a, const int8_t* w, cudaStream_t 
   static uint64_t attr_mask = 0;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), C::SMEM_BYTES, &attr_mask)) return rc;
   const int grid = a.num_m_tiles < num_sms() ? a.num_m_tiles : num_sms();
-  kernel<<<grid, LD_THREADS, C::SMEM_BYTES, s>>>(map_w, a);
+  kernel<<<grid, LD_THREADS, C::SMEM_BYTES, s>>>(map_x, map_w, a);
   return launched("linear_dynamic_tc_kernel");
 }
 

@@ -19,7 +19,7 @@ int copy_tap(uint8_t* const* taps, int idx, const void* src, int64_t bytes, cuda
 
 extern "C" int64_t b200q_static_workspace_bytes(int64_t b) {
   if (b < 0) return B200Q_ERR_INVALID_ARG;
-  return 2 * align_up(b * BYTES_PER_IMG, 1024) + 1024;
+  return 2 * align_up(b * BYTES_PER_IMG, 1024) + 1024 /*alignment slack*/ + 1024 /*ticket word of the small-batch head*/;
 }
 
 namespace {
@@ -31,7 +31,6 @@ const char* const kStageNamesFused[] = {"conv1_conv2_pool", "conv3", "conv4_pool
 const char* const kStageNamesSplit[] = {"quant_conv1", "conv2_pool", "conv3", "conv4_pool",
                                         "conv5",       "conv6_pool", "fc1",   "fc2_dequant"};
 constexpr int kMaxStages = 8;
-constexpr int kGraphKernels = 8;  // kernels one replay of a captured forward launches (b200q_launch_count bookkeeping)
 
 bool fuse12_enabled() {
 #ifndef B200Q_DEV
@@ -53,9 +52,11 @@ bool fuse12_ok(const b200q_static_net* net) {
 
 // taps == nullptr: production path, 2x2 max-pools fused into the conv2/conv4/conv6 epilogues (8 kernels).
 // taps != nullptr: parity path, every reference op materialised (unfused convs + stand-alone pools) and copied out.
+// ticket_is_zero: the caller guarantees the head kernel's ticket word (last 1 KiB of the workspace) already holds 0 (a
+// captured graph: it was zeroed before the capture and every forward leaves it zero); otherwise it is cleared here.
 int forward_impl(const b200q_static_net* net, const float* x, float* logits, int64_t b, void* workspace,
                  int64_t workspace_bytes, uint8_t* const* taps, cudaEvent_t* ev, void* stream,
-                 const uint8_t* x_u8 = nullptr, const uint8_t* lut_host = nullptr) {
+                 const uint8_t* x_u8 = nullptr, const uint8_t* lut_host = nullptr, bool ticket_is_zero = false) {
   B200Q_REQUIRE(net && (((x || x_u8) && logits && workspace) || b == 0), "static_forward: null pointer");
   B200Q_REQUIRE(b >= 0, "static_forward: negative batch");
   if (b == 0) return 0;
@@ -93,6 +94,13 @@ int forward_impl(const b200q_static_net* net, const float* x, float* logits, int
     MARK();
     STEP(b200q_conv3x3_tc(A, B, b, &net->conv[5], 1, stream));  // -> [b,4,4,256]
     MARK();
+    if (!ev) {  // (the profiled forward keeps the two-kernel head: its stage list is fixed)
+      // small batches: fc1 + ReLU + fc2 + dequantize as ONE launch (simt.cu fc_head_small_kernel)
+      unsigned int* ticket = reinterpret_cast<unsigned int*>(B + align_up(b * BYTES_PER_IMG, 1024));
+      int hrc = 0;
+      if (b <= 32 && !ticket_is_zero) B200Q_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
+      if (fc_head_small_dispatch(B, A, logits, ticket, b, &net->fc1, &net->fc2, net->out_scale, s, &hrc) == 0) return hrc;
+    }
     STEP(b200q_linear_tc(B, A, b, &net->fc1, stream));
     MARK();
     STEP(b200q_linear_dequant(A, logits, b, &net->fc2, net->out_scale, stream));
@@ -147,6 +155,7 @@ struct b200q_graph {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   int64_t batch = 0;
+  int kernels = 0;  // kernels one replay launches (b200q_launch_count bookkeeping)
 };
 
 extern "C" int b200q_graph_create(const b200q_static_net* net, const float* x_static, float* logits_static, int64_t b,
@@ -160,10 +169,13 @@ extern "C" int b200q_graph_create(const b200q_static_net* net, const float* x_st
   // does not belong inside a capture
   int rc = forward_impl(net, x_static, logits_static, b, workspace, workspace_bytes, nullptr, nullptr, stream);
   if (rc) return rc;
-  B200Q_CUDA(cudaStreamSynchronize(s));
+  B200Q_CUDA(cudaStreamSynchronize(s));  // (the eager forward above left the head kernel's ticket word zero)
   B200Q_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   pdl_set((flags & B200Q_GRAPH_PDL) != 0);
-  rc = forward_impl(net, x_static, logits_static, b, workspace, workspace_bytes, nullptr, nullptr, stream);
+  const uint64_t launches0 = b200q_launch_count();
+  rc = forward_impl(net, x_static, logits_static, b, workspace, workspace_bytes, nullptr, nullptr, stream, nullptr, nullptr,
+                    /*ticket_is_zero=*/true);
+  const int captured_kernels = (int)(b200q_launch_count() - launches0);
   pdl_set(false);
   cudaGraph_t graph = nullptr;
   const cudaError_t e = cudaStreamEndCapture(s, &graph);  // always end the capture, also after a failed enqueue
@@ -181,6 +193,7 @@ extern "C" int b200q_graph_create(const b200q_static_net* net, const float* x_st
   }
   g->graph = graph;
   g->batch = b;
+  g->kernels = captured_kernels;
   if (int irc = check_cuda(cudaGraphInstantiate(&g->exec, graph, 0), "cudaGraphInstantiate")) {
     cudaGraphDestroy(graph);
     delete g;
@@ -193,7 +206,7 @@ extern "C" int b200q_graph_create(const b200q_static_net* net, const float* x_st
 extern "C" int b200q_graph_launch(b200q_graph* g, void* stream) {
   B200Q_REQUIRE(g && g->exec, "graph_launch: null graph");
   B200Q_CUDA(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
-  note_graph_replay(g->batch == 0 ? 0 : kGraphKernels);
+  note_graph_replay(g->kernels);
   return 0;
 }
 

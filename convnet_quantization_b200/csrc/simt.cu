@@ -252,6 +252,122 @@ __global__ void __launch_bounds__(256) linear_head_dequant_kernel(const LinearAr
   }
 }
 
+// =========================================================================================================
+// Small-batch classifier head (whole-network executor, b <= FC_SMALL_MAX_B): fc1 (+ReLU) and fc2 + dequantize in ONE
+// launch.  At batch 1 the tensor-core fc1 kernel is a chain of 128 dependent-ish MMAs behind a 256 KB weight stream on
+// eight SMs, followed by a second launch for ten dot products; here all 2 MB of fc1 weights are read once, 16 KB per
+// CTA on 128 SMs, by dp4a:
+//   * CTA c owns output channels 4c..4c+3; thread t holds bytes [16t, 16t+16) of those four weight rows in registers
+//     (256 threads x 16 B = K = 4096) and of up to FC_G image rows at a time; 16 dot products per thread, REDUX across
+//     the warp, eight warp partials through shared memory, exact fbgemm requantisation, one byte per (image, channel);
+//   * the CTA that finishes LAST (a ticket in the caller's workspace, reset by that CTA) runs fc2 + dequantize on the
+//     512-byte rows all CTAs wrote (read through L2), one warp per image as in linear_head_dequant_kernel.
+// Integer accumulation is exact in any order, so the result is bit-identical to the two-kernel path.
+constexpr int FC_SMALL_MAX_B = 32;
+constexpr int FC_G = 4;  // images per pass
+
+struct FcSmallArgs {
+  const uint8_t* x;       // [b][4096] uint8 (NHWC-flattened pool3 output)
+  uint8_t* h;             // [b][512] scratch: fc1 output
+  float* logits;          // [b][10]
+  unsigned int* ticket;   // zero on entry, zero on exit
+  const int8_t* w1;       // [512][4096]
+  const int32_t* corr1;
+  const float* mult1;
+  const float* bdiv1;
+  const int8_t* w2;       // [10][512]
+  const int32_t* corr2;
+  const float* mult2;
+  const float* bdiv2;
+  int b;
+  int zp1, lo1;           // fc1 output zero-point, lower clamp (ReLU: zp1)
+  int zp2, lo2;
+  float out_scale;
+};
+
+__global__ void __launch_bounds__(256) fc_head_small_kernel(const FcSmallArgs a) {
+  constexpr int K = 4096, N1 = 512, N2 = 10, CH = 4;
+  __shared__ int s_part[8][FC_G * CH];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c0 = blockIdx.x * CH;
+  pdl_launch_dependents();
+  uint4 w[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) w[c] = __ldg(reinterpret_cast<const uint4*>(a.w1 + (int64_t)(c0 + c) * K) + tid);
+  uint4 w2[N2];  // every CTA prefetches fc2's 5 KB (only the last one uses them): hides the load behind fc1
+#pragma unroll
+  for (int n = 0; n < N2; ++n) w2[n] = __ldg(reinterpret_cast<const uint4*>(a.w2 + n * N1) + lane);
+  pdl_wait();  // x is the previous kernel's output
+  for (int i0 = 0; i0 < a.b; i0 += FC_G) {
+    uint4 xv[FC_G];
+#pragma unroll
+    for (int g = 0; g < FC_G; ++g)
+      xv[g] = (i0 + g < a.b) ? __ldg(reinterpret_cast<const uint4*>(a.x + (int64_t)(i0 + g) * K) + tid) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int g = 0; g < FC_G; ++g)
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        int acc = dp4a_us(xv[g].x, w[c].x, 0);
+        acc = dp4a_us(xv[g].y, w[c].y, acc);
+        acc = dp4a_us(xv[g].z, w[c].z, acc);
+        acc = dp4a_us(xv[g].w, w[c].w, acc);
+        acc = __reduce_add_sync(0xffffffffu, acc);
+        if (lane == 0) s_part[warp][g * CH + c] = acc;
+      }
+    __syncthreads();
+    if (tid < FC_G * CH && i0 + tid / CH < a.b) {
+      int acc = 0;
+#pragma unroll
+      for (int wi = 0; wi < 8; ++wi) acc += s_part[wi][tid];
+      const int ch = c0 + tid % CH;
+      a.h[(int64_t)(i0 + tid / CH) * N1 + ch] =
+          (uint8_t)requant_u8(acc - __ldg(a.corr1 + ch), __ldg(a.bdiv1 + ch), __ldg(a.mult1 + ch), a.zp1, a.lo1);
+    }
+    __syncthreads();
+  }
+  // ---- ticket: the last CTA to get here sees every other CTA's h rows (release: fence + atomic; acquire: fence)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int nn = lane < N2 ? lane : 0;
+  const int corr = __ldg(a.corr2 + nn);
+  const float bdiv = __ldg(a.bdiv2 + nn), mult = __ldg(a.mult2 + nn);
+  for (int img = warp; img < a.b; img += 8) {
+    const uint4 x = __ldcg(reinterpret_cast<const uint4*>(a.h + (int64_t)img * N1) + lane);  // written by other SMs: L2
+    int mine = 0;
+#pragma unroll
+    for (int n = 0; n < N2; ++n) {
+      int acc = dp4a_us(x.x, w2[n].x, 0);
+      acc = dp4a_us(x.y, w2[n].y, acc);
+      acc = dp4a_us(x.z, w2[n].z, acc);
+      acc = dp4a_us(x.w, w2[n].w, acc);
+      acc = __reduce_add_sync(0xffffffffu, acc);
+      if (lane == n) mine = acc;
+    }
+    if (lane < N2) {
+      const uint32_t q = requant_u8(mine - corr, bdiv, mult, a.zp2, a.lo2);
+      a.logits[img * N2 + lane] = __fmul_rn(__int2float_rn((int)q - a.zp2), a.out_scale);
+    }
+  }
+  if (tid == 0) *a.ticket = 0u;  // ready for the next forward on this workspace
+}
+
+// Returns 1 when the pair of layers / the batch is not the shape this kernel is written for.
+int fc_head_small_dispatch(const uint8_t* x, uint8_t* h, float* logits, unsigned int* ticket, int64_t b,
+                           const b200q_linear* fc1, const b200q_linear* fc2, float out_scale, cudaStream_t s, int* rc) {
+  if (b < 1 || b > FC_SMALL_MAX_B || fc1->k != 4096 || fc1->n != 512 || fc2->k != 512 || fc2->n != 10) return 1;
+  if ((uintptr_t)x % 16 || (uintptr_t)h % 16 || (uintptr_t)fc1->w % 16 || (uintptr_t)fc2->w % 16 || (uintptr_t)ticket % 4) return 1;
+  FcSmallArgs a{x, h, logits, ticket, fc1->w, fc1->corr, fc1->rq.mult, fc1->rq.bdiv, fc2->w, fc2->corr, fc2->rq.mult,
+                fc2->rq.bdiv, (int)b, fc1->rq.zp_out, fc1->rq.relu ? fc1->rq.zp_out : 0, fc2->rq.zp_out,
+                fc2->rq.relu ? fc2->rq.zp_out : 0, out_scale};
+  *rc = launch_kernel("fc_head_small_kernel", fc_head_small_kernel, 512 / 4, 256, 0, s, a);
+  return 0;
+}
+
 template <int EPI>
 static int launch_linear(const LinearArgs& a, cudaStream_t s) {
   dim3 grid((unsigned)((a.b + 63) / 64), (unsigned)((a.n + 63) / 64));

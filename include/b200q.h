@@ -164,7 +164,8 @@ int b200q_linear_dequant(const uint8_t* x, float* y, int64_t b, const b200q_line
 /* quantized::linear_dynamic(x, W, reduce_range=True) (models/dynamic_ptq_model.py:302-306 -> nnqd.Linear), two launches:
  * (1) per-tensor min/max of the WHOLE input -> (scale, zp) on device (b200q_minmax); (2) one tcgen05 GEMM kernel whose
  * producer warps quantise the fp32 rows straight into the swizzled K-major shared-memory tiles the tensor core reads
- * (the uint8 activations never exist in HBM), weights by TMA, epilogue y = f32(acc - zp*wsum[n]) * (s_x*s_w) + bias[n]
+ * (the uint8 activations never exist in HBM), weights by TMA.  Arithmetic is fbgemm's, bit for bit:
+ * x_q = clamp(rne(fma(x, 1/s_x, zp)), 0, 255) and y = fma(f32(acc - zp*wsum[n]), fl32(s_x*s_w), bias[n])
  * (+ ReLU when relu != 0, the F.relu that follows fc1 at models/baseline_model.py:80).
  * x fp32 [b,k] (k % 64 == 0); w int8 [n][k], per-tensor symmetric scale w_scale, n == 512 or n <= 16;
  * wsum[n] = sum_k w; bias fp32 [n]; y fp32 [b,n].  scratch: B200Q_REDUCE_SCRATCH_BYTES (its qparams block is left

@@ -154,7 +154,10 @@ def linear_dynamic(x_f32: np.ndarray, w_int8: np.ndarray, w_scale: float, bias: 
     inv = F32(1.0) / s_x
     xq = np.clip(np.rint((x.astype(np.float64) * np.float64(inv) + np.float64(zp)).astype(F32)).astype(np.int64), 0, 255)
     acc = ((xq - zp).astype(np.float64) @ w_int8.astype(np.float64).T)
-    return (acc.astype(F32) * F32(s_x * F32(w_scale)) + bias.astype(F32)).astype(F32)
+    # output stage: ONE fused multiply-add fma(f32(acc), fl32(s_x * s_w), bias) (|acc| < 2^29, so the float64 product and
+    # sum below are exact and the final cast is the fma's single rounding); bit-identical to the live op
+    s_xw = np.float64(F32(s_x * F32(w_scale)))
+    return (acc.astype(F32).astype(np.float64) * s_xw + bias.astype(F32).astype(np.float64)).astype(F32)
 
 
 def static_forward(x_f32_nchw: np.ndarray, qp: dict, taps: dict | None = None) -> np.ndarray:

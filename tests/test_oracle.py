@@ -63,7 +63,7 @@ def test_linear_dynamic_restatement(b, k, n):
     want = qlin(x).numpy()
     w = qlin.weight()
     got = IO.linear_dynamic(x.numpy(), w.int_repr().numpy(), w.q_scale(), qlin.bias().detach().numpy())
-    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+    assert np.array_equal(got, want)  # BIT-exact: fma activation quantisation + fma output stage (fbgemm's own forms)
 
 
 def test_dynamic_qparams_restatement_vs_torch():
@@ -175,5 +175,5 @@ def test_dynamic_activation_quantisation_is_a_fused_multiply_add():
         mism["fma"] += int((fma != xq).sum())
         mism["mul_then_add_int"] += int((mul != xq).sum())
         got = IO.linear_dynamic(xn, w.int_repr().numpy(), w.q_scale(), np.zeros(k, np.float32))
-        np.testing.assert_allclose(got, y, rtol=1e-6, atol=1e-6 * np.abs(y).max())
+        assert np.array_equal(got, y)
     assert mism["fma"] == 0 and mism["mul_then_add_int"] > 0, mism
