@@ -257,14 +257,15 @@ __global__ void __launch_bounds__(256) linear_head_dequant_kernel(const LinearAr
 // launch.  At batch 1 the tensor-core fc1 kernel is a chain of 128 dependent-ish MMAs behind a 256 KB weight stream on
 // eight SMs, followed by a second launch for ten dot products; here all 2 MB of fc1 weights are read once, 16 KB per
 // CTA on 128 SMs, by dp4a:
-//   * CTA c owns output channels 4c..4c+3; thread t holds bytes [16t, 16t+16) of those four weight rows in registers
-//     (256 threads x 16 B = K = 4096) and of up to FC_G image rows at a time; 16 dot products per thread, REDUX across
-//     the warp, eight warp partials through shared memory, exact fbgemm requantisation, one byte per (image, channel);
+//   * CTA c owns output channels 4c..4c+3 and keeps their four weight rows (16 KB) in shared memory - loaded BEFORE the
+//     programmatic-dependent-launch wait, i.e. while the previous layer is still running;
+//   * a warp takes one image at a time: its 4 KB row as eight 16-byte loads per lane (all in flight at once, the next
+//     image's issued before this one is reduced), 4 x 32 dp4a per lane, REDUX across the warp, exact fbgemm
+//     requantisation, one byte per (image, channel).  No block-wide synchronisation in the loop;
 //   * the CTA that finishes LAST (a ticket in the caller's workspace, reset by that CTA) runs fc2 + dequantize on the
 //     512-byte rows all CTAs wrote (read through L2), one warp per image as in linear_head_dequant_kernel.
 // Integer accumulation is exact in any order, so the result is bit-identical to the two-kernel path.
-constexpr int FC_SMALL_MAX_B = 32;
-constexpr int FC_G = 4;  // images per pass
+constexpr int FC_SMALL_MAX_B = 64;
 
 struct FcSmallArgs {
   const uint8_t* x;       // [b][4096] uint8 (NHWC-flattened pool3 output)
@@ -286,45 +287,49 @@ struct FcSmallArgs {
 };
 
 __global__ void __launch_bounds__(256) fc_head_small_kernel(const FcSmallArgs a) {
-  constexpr int K = 4096, N1 = 512, N2 = 10, CH = 4;
-  __shared__ int s_part[8][FC_G * CH];
+  constexpr int K = 4096, N1 = 512, N2 = 10, CH = 4, KV = K / 16 / 32;  // KV: 16-byte vectors per lane and row
+  __shared__ uint4 s_w[CH][K / 16];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c0 = blockIdx.x * CH;
   pdl_launch_dependents();
-  uint4 w[CH];
 #pragma unroll
-  for (int c = 0; c < CH; ++c) w[c] = __ldg(reinterpret_cast<const uint4*>(a.w1 + (int64_t)(c0 + c) * K) + tid);
+  for (int c = 0; c < CH; ++c) s_w[c][tid] = __ldg(reinterpret_cast<const uint4*>(a.w1 + (int64_t)(c0 + c) * K) + tid);
   uint4 w2[N2];  // every CTA prefetches fc2's 5 KB (only the last one uses them): hides the load behind fc1
 #pragma unroll
   for (int n = 0; n < N2; ++n) w2[n] = __ldg(reinterpret_cast<const uint4*>(a.w2 + n * N1) + lane);
+  const int myc = c0 + (lane & 3);
+  const int corr1 = __ldg(a.corr1 + myc);
+  const float bdiv1 = __ldg(a.bdiv1 + myc), mult1 = __ldg(a.mult1 + myc);
   pdl_wait();  // x is the previous kernel's output
-  for (int i0 = 0; i0 < a.b; i0 += FC_G) {
-    uint4 xv[FC_G];
+  __syncthreads();
+  auto load_row = [&](uint4 (&v)[KV], int img) {
 #pragma unroll
-    for (int g = 0; g < FC_G; ++g)
-      xv[g] = (i0 + g < a.b) ? __ldg(reinterpret_cast<const uint4*>(a.x + (int64_t)(i0 + g) * K) + tid) : make_uint4(0, 0, 0, 0);
+    for (int j = 0; j < KV; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(a.x + (int64_t)img * K) + j * 32 + lane);
+  };
+  uint4 cur[KV], nxt[KV];
+  if (warp < a.b) load_row(cur, warp);
+  for (int img = warp; img < a.b; img += 8) {
+    if (img + 8 < a.b) load_row(nxt, img + 8);
+    int acc[CH] = {0, 0, 0, 0};
 #pragma unroll
-    for (int g = 0; g < FC_G; ++g)
+    for (int j = 0; j < KV; ++j)
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
-        int acc = dp4a_us(xv[g].x, w[c].x, 0);
-        acc = dp4a_us(xv[g].y, w[c].y, acc);
-        acc = dp4a_us(xv[g].z, w[c].z, acc);
-        acc = dp4a_us(xv[g].w, w[c].w, acc);
-        acc = __reduce_add_sync(0xffffffffu, acc);
-        if (lane == 0) s_part[warp][g * CH + c] = acc;
+        const uint4 wv = s_w[c][j * 32 + lane];
+        acc[c] = dp4a_us(cur[j].x, wv.x, acc[c]);
+        acc[c] = dp4a_us(cur[j].y, wv.y, acc[c]);
+        acc[c] = dp4a_us(cur[j].z, wv.z, acc[c]);
+        acc[c] = dp4a_us(cur[j].w, wv.w, acc[c]);
       }
-    __syncthreads();
-    if (tid < FC_G * CH && i0 + tid / CH < a.b) {
-      int acc = 0;
 #pragma unroll
-      for (int wi = 0; wi < 8; ++wi) acc += s_part[wi][tid];
-      const int ch = c0 + tid % CH;
-      a.h[(int64_t)(i0 + tid / CH) * N1 + ch] =
-          (uint8_t)requant_u8(acc - __ldg(a.corr1 + ch), __ldg(a.bdiv1 + ch), __ldg(a.mult1 + ch), a.zp1, a.lo1);
+    for (int c = 0; c < CH; ++c) acc[c] = __reduce_add_sync(0xffffffffu, acc[c]);
+    if (lane < CH) {  // lane c requantises channel c0 + c
+      const int mine = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+      a.h[(int64_t)img * N1 + myc] = (uint8_t)requant_u8(mine - corr1, bdiv1, mult1, a.zp1, a.lo1);
     }
-    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < KV; ++j) cur[j] = nxt[j];
   }
   // ---- ticket: the last CTA to get here sees every other CTA's h rows (release: fence + atomic; acquire: fence)
   __threadfence();
