@@ -98,7 +98,7 @@ int forward_impl(const b200q_static_net* net, const float* x, float* logits, int
       // small batches: fc1 + ReLU + fc2 + dequantize as ONE launch (simt.cu fc_head_small_kernel)
       unsigned int* ticket = reinterpret_cast<unsigned int*>(B + align_up(b * BYTES_PER_IMG, 1024));
       int hrc = 0;
-      if (b <= 64 && !ticket_is_zero) B200Q_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
+      if (b <= 32 && !ticket_is_zero) B200Q_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
       if (fc_head_small_dispatch(B, A, logits, ticket, b, &net->fc1, &net->fc2, net->out_scale, s, &hrc) == 0) return hrc;
     }
     STEP(b200q_linear_tc(B, A, b, &net->fc1, stream));

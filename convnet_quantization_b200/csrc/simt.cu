@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) linear_head_dequant_kernel(const LinearAr
 //   * the CTA that finishes LAST (a ticket in the caller's workspace, reset by that CTA) runs fc2 + dequantize on the
 //     512-byte rows all CTAs wrote (read through L2), one warp per image as in linear_head_dequant_kernel.
 // Integer accumulation is exact in any order, so the result is bit-identical to the two-kernel path.
-constexpr int FC_SMALL_MAX_B = 64;
+constexpr int FC_SMALL_MAX_B = 32;  // measured: ahead of the two-kernel head up to 32 images, behind it at 64 (r02 sweep)
 
 struct FcSmallArgs {
   const uint8_t* x;       // [b][4096] uint8 (NHWC-flattened pool3 output)

@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 warnings.filterwarnings("ignore")
 import torch
 from convnet_quantization_b200 import synth
-from convnet_quantization_b200.engine import StaticEngine, _Graph
+from convnet_quantization_b200.engine import _Graph
 from convnet_quantization_b200.models.static_ptq_model import StaticPTQModel
 
 ap = argparse.ArgumentParser()

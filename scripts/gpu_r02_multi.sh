@@ -6,9 +6,9 @@ mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo_n$N.txt 2>&1
 lscpu | grep -E "Model name|^CPU\(s\)|NUMA|Socket" > gpurun_out/host_n$N.txt; nproc >> gpurun_out/host_n$N.txt; cat /sys/fs/cgroup/cpuset.cpus.effective >> gpurun_out/host_n$N.txt 2>/dev/null
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 300 $TR --master-port 29511 scripts/h2d_probe.py > gpurun_out/h2d_n$N.json 2> gpurun_out/h2d_n$N.err; echo "h2d exit=$?"; python -c "
+timeout 300 $TR --master-port 29511 scripts/h2d_probe.py --out=gpurun_out/h2d_n$N.json > gpurun_out/h2d_n$N.log 2> gpurun_out/h2d_n$N.err; echo "h2d exit=$?"; python -c "
 import json; d=json.load(open('gpurun_out/h2d_n$N.json')); print(d['aggregate_gbs'], d['min_per_gpu_gbs']); print([r['numa'] for r in d['ranks']][:2])"
-timeout 300 $TR --master-port 29512 scripts/h2d_probe.py --no-bind > gpurun_out/h2d_n${N}_nobind.json 2> gpurun_out/h2d_n${N}_nobind.err; echo "h2d nobind exit=$?"; python -c "
+timeout 300 $TR --master-port 29512 scripts/h2d_probe.py --no-bind --out=gpurun_out/h2d_n${N}_nobind.json > gpurun_out/h2d_n${N}_nobind.log 2> gpurun_out/h2d_n${N}_nobind.err; echo "h2d nobind exit=$?"; python -c "
 import json; d=json.load(open('gpurun_out/h2d_n${N}_nobind.json')); print(d['aggregate_gbs'], d['min_per_gpu_gbs'])"
 timeout 600 $TR --master-port 29513 bench.py --gpus $N --steps 20 --warmup 5 --sustain-s 0 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench exit=$?"; python -c "
 import json; d=json.load(open('gpurun_out/bench_n$N.json')); print('value', d['value'], 'e2e', d['e2e']['value'], 'e2e_u8', d['e2e_u8']['value'], d['parity'], d['eval'])"; tail -2 gpurun_out/bench_n$N.err

@@ -3,7 +3,7 @@ own GPU at the same time, plain cudaMemcpyAsync loops; rank 0 prints one JSON ob
     python scripts/h2d_probe.py                      (N = 1)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 scripts/h2d_probe.py
 The ceiling this measures is what the fp32-input e2e number of bench.py can reach: 12 288 B per image over this link."""
-import json, os, sys, time
+import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
@@ -34,7 +34,6 @@ for name, nbytes in (("fp32_batch_192MiB", 16384 * 12288), ("uint8_batch_48MiB",
     e1.record()
     torch.cuda.synchronize()
     gbs = nbytes * iters / (e0.elapsed_time(e1) * 1e-3) / 1e9
-    d2h = torch.empty(655360, dtype=torch.uint8).pin_memory()
     res[name] = gbs
     if world > 1:
         dist.barrier()
@@ -51,6 +50,10 @@ if rank == 0:
            "min_per_gpu_gbs": {k: min(r["h2d_gbs"][k] for r in allr) for k in res},
            "fp32_e2e_ceiling_images_per_s": sum(r["h2d_gbs"]["fp32_batch_192MiB"] for r in allr) * 1e9 / 12288,
            "uint8_e2e_ceiling_images_per_s": sum(r["h2d_gbs"]["uint8_batch_48MiB"] for r in allr) * 1e9 / 3072}
+    dst = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")]
+    if dst:  # NCCL prints its banner on stdout: a file keeps the JSON clean
+        with open(dst[0], "w") as f:
+            json.dump(out, f, indent=1)
     print(json.dumps(out))
 if world > 1:
     dist.destroy_process_group()
