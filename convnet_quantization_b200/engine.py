@@ -1,6 +1,7 @@
 """Device engine for the static-PTQ SimpleConvNet: packed weights + workspace + the single C-ABI forward call."""
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from collections import OrderedDict
 
@@ -15,6 +16,9 @@ TAP_SHAPES = {  # per image, NHWC (quant is NHWC4: channel 3 is padding)
     "conv3": (16, 16, 128), "conv4": (16, 16, 128), "pool2": (8, 8, 128), "conv5": (8, 8, 256),
     "conv6": (8, 8, 256), "pool3": (4, 4, 256), "fc1": (512,), "fc2": (10,),
 }
+
+
+_NULL_CTX = contextlib.nullcontext()
 
 
 class _Graph:
@@ -141,7 +145,10 @@ class StaticEngine:
         self._check_input(x, (3, 32, 32), torch.float32, "StaticEngine.forward")
         b = x.shape[0]
         self._check_out(out, b)
-        with torch.cuda.device(self.device):
+        # small batches are latency-bound down to the Python level: skip the device context manager when the engine's
+        # device is already current (the common, single-GPU-per-process case)
+        ctx = _NULL_CTX if torch.cuda.current_device() == self.device.index else torch.cuda.device(self.device)
+        with ctx:
             if b == 0:
                 logits = out if out is not None else torch.empty((0, 10), dtype=torch.float32, device=self.device)
                 return (logits, {}) if taps else logits

@@ -156,3 +156,50 @@ def test_histogram_observer_on_gpu_equals_cpu_observer():
     s0, z0 = cpu.calculate_qparams()
     s1, z1 = gpu.calculate_qparams()
     assert torch.equal(s0, s1) and torch.equal(z0, z1)
+
+
+def test_c_abi_argument_errors_are_status_codes_not_faults():
+    """Bad arguments at the C boundary return a negative status with a message (include/b200q.h conventions)."""
+    import ctypes as C
+    from convnet_quantization_b200 import _lib
+    lib = _lib.load()
+    x = torch.zeros(128, 4096, device="cuda")
+    y = torch.zeros(128, 512, device="cuda")
+    w = torch.zeros(512, 4096, dtype=torch.int8, device="cuda")
+    ws = torch.zeros(512, dtype=torch.int32, device="cuda")
+    bias = torch.zeros(512, device="cuda")
+    scratch = torch.zeros(_lib.REDUCE_SCRATCH_BYTES // 4, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    args = (x.data_ptr(), y.data_ptr(), 128, 4096, 512, w.data_ptr(), ws.data_ptr(), 0.01, bias.data_ptr(), 0, scratch.data_ptr())
+    assert lib.b200q_linear_dynamic(*args, _lib.REDUCE_SCRATCH_BYTES, s) == 0
+    assert lib.b200q_linear_dynamic(*args, 8208, s) == -1                       # the size round 1's header documented: too small
+    assert b"scratch too small" in lib.b200q_last_error()
+    bad_n = list(args)
+    bad_n[4] = 100
+    assert lib.b200q_linear_dynamic(*bad_n, _lib.REDUCE_SCRATCH_BYTES, s) == -1  # n must be 512 or <= 16
+    hist = torch.zeros(8192, dtype=torch.int64, device="cuda")
+    assert lib.b200q_histc(x.data_ptr(), x.numel(), 0.0, 1.0, 8192, hist.data_ptr(), s) == -1  # bins > 4096
+    assert lib.b200q_histc(x.data_ptr(), x.numel(), 1.0, 1.0, 16, hist.data_ptr(), s) == -1    # lo == hi
+    assert lib.b200q_lut_u8(x.data_ptr(), y.data_ptr(), 16, None, s) == -1
+    g = C.c_void_p()
+    assert lib.b200q_graph_create(None, x.data_ptr(), y.data_ptr(), 4, scratch.data_ptr(), 1 << 20, 0, s, C.byref(g)) == -1
+    assert lib.b200q_graph_launch(None, s) == -1
+    assert lib.b200q_graph_destroy(None) == 0
+    torch.cuda.synchronize()
+
+
+def test_graph_capture_refuses_the_legacy_default_stream(qparams):
+    import ctypes as C
+    from convnet_quantization_b200 import _lib
+    from convnet_quantization_b200.engine import StaticEngine
+    eng = StaticEngine(qparams, "cuda")
+    x = torch.zeros(4, 3, 32, 32, device="cuda")
+    y = torch.zeros(4, 10, device="cuda")
+    ws = torch.empty(int(eng.lib.b200q_static_workspace_bytes(4)), dtype=torch.uint8, device="cuda")
+    g = C.c_void_p()
+    rc = eng.lib.b200q_graph_create(eng.packed.ptr(), x.data_ptr(), y.data_ptr(), 4, ws.data_ptr(), ws.numel(), 0, None, C.byref(g))
+    assert rc == -1 and b"legacy default stream" in eng.lib.b200q_last_error() and not g.value
+    rc = eng.lib.b200q_graph_create(eng.packed.ptr(), x.data_ptr(), y.data_ptr(), 4, ws.data_ptr(), 100, _lib.GRAPH_PDL,
+                                    torch.cuda.Stream().cuda_stream, C.byref(g))
+    assert rc == -1 and b"workspace too small" in eng.lib.b200q_last_error()
+    torch.cuda.synchronize()
