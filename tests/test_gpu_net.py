@@ -235,3 +235,17 @@ def test_engine_rejects_foreign_tensors(qparams):
     if torch.cuda.device_count() > 1:
         with pytest.raises(_lib.B200QError):
             eng.forward(torch.zeros(4, 3, 32, 32, device="cuda:1"))
+
+
+@pytest.mark.parametrize("b", [18, 19, 32, 33, 37, 38, 74, 75, 148, 149])
+def test_kernel_selection_thresholds_are_bit_exact(engine, oracle_model, b):
+    """Every batch size at which b200q_conv3x3_tc / b200q_linear_tc / the forward switch kernels (small-batch N-tile-64
+    tiles <-> band-resident kernels per layer: 37|38, 74|75, 148|149; fused head <-> two-kernel head: 32|33; fc1 tile
+    shape) - logits vs the CPU oracle, eager and as a CUDA graph."""
+    from convnet_quantization_b200 import synth
+    from oracle import torch_oracle as TO
+    x = synth.images_f32(b, seed=900 + b)
+    want, _ = TO.run_static_oracle(oracle_model, x)
+    xd = x.cuda()
+    assert torch.equal(engine.forward(xd, graph=False).cpu(), want)
+    assert torch.equal(engine.forward(xd, graph=True).cpu(), want)
