@@ -43,9 +43,12 @@ class _Graph:
         _lib.check(self.lib.b200q_graph_launch(self.handle, stream), "graph_launch")
 
     def __del__(self):
-        if getattr(self, "handle", None):
-            self.lib.b200q_graph_destroy(self.handle)
-            self.handle = None
+        try:  # may run during interpreter shutdown, after the library or the CUDA context is gone
+            if getattr(self, "handle", None):
+                self.lib.b200q_graph_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
 
 
 class StaticEngine:

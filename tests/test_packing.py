@@ -94,3 +94,27 @@ def test_input_lut_is_the_reference_pipeline_on_every_pixel_value():
     # monotone in the pixel value, and the explicit-mean/std form agrees with the default
     assert bool((lut[:, 1:].int() >= lut[:, :-1].int()).all())
     assert torch.equal(input_lut(scale, zp, synth.CIFAR_MEAN, synth.CIFAR_STD), lut)
+
+
+def test_prepack_handles_keep_their_objects_alive_until_collected(qparams):
+    """torch.ops.b200q.*_prepack return opaque int64 handle tensors (like ATen's packed-params objects); the registry
+    entry lives exactly as long as the handle tensor."""
+    import gc
+    from convnet_quantization_b200 import _lib, ops
+    from convnet_quantization_b200.packing import PackedConv, PackedLinear
+    L = qparams["conv2"]
+    h = torch.ops.b200q.conv_prepack(L["w_int8"], L["w_scales"], L["bias"], qparams["conv1"]["out_scale"],
+                                     qparams["conv1"]["out_zp"], L["out_scale"], L["out_zp"], True, "cpu")
+    assert h.dtype == torch.int64 and h.numel() == 1
+    pc = ops._packed(h, PackedConv)
+    assert (pc.cin, pc.cout, pc.img) == (64, 64, 32) and pc.c.rq.relu == 1
+    with pytest.raises(_lib.B200QError):
+        ops._packed(h, PackedLinear)  # wrong kind of handle
+    key = int(h.item())
+    assert key in ops._handles
+    del h, pc
+    gc.collect()
+    assert key not in ops._handles
+    with pytest.raises(_lib.B200QError):
+        torch.ops.b200q.conv_prepack(torch.zeros(7, 5, 3, 3, dtype=torch.int8), torch.ones(7, dtype=torch.float64),
+                                     torch.zeros(7), 0.1, 0, 0.1, 0, True, "cpu")  # no kernel for that geometry
