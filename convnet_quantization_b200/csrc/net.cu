@@ -31,6 +31,7 @@ const char* const kStageNamesFused[] = {"conv1_conv2_pool", "conv3", "conv4_pool
 const char* const kStageNamesSplit[] = {"quant_conv1", "conv2_pool", "conv3", "conv4_pool",
                                         "conv5",       "conv6_pool", "fc1",   "fc2_dequant"};
 constexpr int kMaxStages = 8;
+constexpr bool kEagerPdlDefault = false;
 
 bool fuse12_enabled() {
 #ifndef B200Q_DEV
@@ -52,8 +53,34 @@ bool fuse12_ok(const b200q_static_net* net) {
 
 // taps == nullptr: production path, 2x2 max-pools fused into the conv2/conv4/conv6 epilogues (8 kernels).
 // taps != nullptr: parity path, every reference op materialised (unfused convs + stand-alone pools) and copied out.
-// ticket_is_zero: the caller guarantees the head kernel's ticket word (last 1 KiB of the workspace) already holds 0 (a
-// captured graph: it was zeroed before the capture and every forward leaves it zero); otherwise it is cleared here.
+// Programmatic dependent launch between the kernels of an EAGER forward (not only inside captured graphs): each layer
+// kernel's prologue (up to 144 KB of weights into shared memory per CTA, TMEM allocation, pad initialisation) then
+// overlaps the tail of the previous layer.  Development builds: B200Q_EAGER_PDL=0|1 overrides (A-B timing).
+bool eager_pdl() {
+#ifdef B200Q_DEV
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200Q_EAGER_PDL");
+    v = e ? (e[0] == '1') : kEagerPdlDefault;
+  }
+  return v == 1;
+#else
+  return kEagerPdlDefault;
+#endif
+}
+struct PdlScope {  // sets the thread's PDL launch flag for the lifetime of the scope
+  bool prev, active;
+  explicit PdlScope(bool on) : prev(pdl_enabled()), active(on) {
+    if (active) pdl_set(true);
+  }
+  ~PdlScope() {
+    if (active) pdl_set(prev);
+  }
+};
+
+// ticket_is_zero: the caller is capturing a graph and guarantees the head kernel's ticket word (last 1 KiB of the
+// workspace) already holds 0 (it was zeroed before the capture and every forward leaves it zero); otherwise it is
+// cleared here.
 int forward_impl(const b200q_static_net* net, const float* x, float* logits, int64_t b, void* workspace,
                  int64_t workspace_bytes, uint8_t* const* taps, cudaEvent_t* ev, void* stream,
                  const uint8_t* x_u8 = nullptr, const uint8_t* lut_host = nullptr, bool ticket_is_zero = false) {
@@ -71,6 +98,7 @@ int forward_impl(const b200q_static_net* net, const float* x, float* logits, int
 #define MARK() do { if (ev) B200Q_CUDA(cudaEventRecord(ev[stage++], s)); } while (0)
 
   if (taps == nullptr) {
+    PdlScope pdl(!ev && !ticket_is_zero && eager_pdl());  // (a capture sets the flag itself, from its B200Q_GRAPH_PDL flag)
     MARK();
     if (x_u8) {  // uint8 data path: table look-up instead of the fp32 quantiser, same kernel otherwise
       STEP(b200q_u8_conv3x3_first(x_u8, A, b, lut_host, &net->conv[0], stream));
