@@ -68,6 +68,9 @@ bool eager_pdl() {
   return kEagerPdlDefault;
 #endif
 }
+#ifdef B200Q_DEV
+thread_local int g_stop_after = 0;
+#endif
 struct PdlScope {  // sets the thread's PDL launch flag for the lifetime of the scope
   bool prev, active;
   explicit PdlScope(bool on) : prev(pdl_enabled()), active(on) {
@@ -94,7 +97,12 @@ int forward_impl(const b200q_static_net* net, const float* x, float* logits, int
   uint8_t* B = A + align_up(b * BYTES_PER_IMG, 1024);
   int rc;
   int stage = 0;
+#ifdef B200Q_DEV  // timing experiments: stop the production forward after g_stop_after kernels (scripts/graph_breakdown.py)
+#define STEP(call) do { rc = (call); if (rc) return rc; if (!taps && g_stop_after && ++steps_done >= g_stop_after) return 0; } while (0)
+  int steps_done = 0;
+#else
 #define STEP(call) do { rc = (call); if (rc) return rc; } while (0)
+#endif
 #define MARK() do { if (ev) B200Q_CUDA(cudaEventRecord(ev[stage++], s)); } while (0)
 
   if (taps == nullptr) {
@@ -127,6 +135,9 @@ int forward_impl(const b200q_static_net* net, const float* x, float* logits, int
       unsigned int* ticket = reinterpret_cast<unsigned int*>(B + align_up(b * BYTES_PER_IMG, 1024));
       int hrc = 0;
       if (b <= 32 && !ticket_is_zero) B200Q_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
+#ifdef B200Q_DEV
+      if (g_stop_after && steps_done >= g_stop_after) return 0;
+#endif
       if (fc_head_small_dispatch(B, A, logits, ticket, b, &net->fc1, &net->fc2, net->out_scale, s, &hrc) == 0) return hrc;
     }
     STEP(b200q_linear_tc(B, A, b, &net->fc1, stream));
@@ -200,11 +211,17 @@ extern "C" int b200q_graph_create(const b200q_static_net* net, const float* x_st
   B200Q_CUDA(cudaStreamSynchronize(s));  // (the eager forward above left the head kernel's ticket word zero)
   B200Q_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   pdl_set((flags & B200Q_GRAPH_PDL) != 0);
+#ifdef B200Q_DEV
+  g_stop_after = (flags >> 8) & 15;  // development library: capture only the first k kernels (timing breakdown)
+#endif
   const uint64_t launches0 = b200q_launch_count();
   rc = forward_impl(net, x_static, logits_static, b, workspace, workspace_bytes, nullptr, nullptr, stream, nullptr, nullptr,
                     /*ticket_is_zero=*/true);
   const int captured_kernels = (int)(b200q_launch_count() - launches0);
   pdl_set(false);
+#ifdef B200Q_DEV
+  g_stop_after = 0;
+#endif
   cudaGraph_t graph = nullptr;
   const cudaError_t e = cudaStreamEndCapture(s, &graph);  // always end the capture, also after a failed enqueue
   if (rc) {
