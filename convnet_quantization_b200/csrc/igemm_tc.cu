@@ -401,6 +401,19 @@ static bool force_streamed() {
   return v == 1;
 }
 
+// -DB200Q_DEV builds only: B200Q_NO_CTA2=1 keeps conv2 on the single-CTA kernel (A-B timing only).
+static bool no_cta2() {
+#ifndef B200Q_DEV
+  return false;
+#endif
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200Q_NO_CTA2");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 // -DB200Q_DEV builds only: B200Q_NO_SMALL=1 disables the small-batch kernel selection (A-B timing only).
 static bool small_batch_off() {
 #ifndef B200Q_DEV
@@ -458,6 +471,7 @@ extern "C" int b200q_conv3x3_tc(const uint8_t* x, uint8_t* y, int64_t b, const b
   }
   if (!no_halo()) {
     int rc = 0;
+    if (!no_cta2() && conv3x3_halo2_dispatch(x, y, b, L, pool, s, &rc) == 0) return rc;
     if (conv3x3_halo_dispatch(x, y, b, L, pool, s, &rc) == 0) return rc;
     if (conv3x3_pair_dispatch(x, y, b, L, pool, s, &rc) == 0) return rc;
   }

@@ -126,7 +126,7 @@ def test_linear_dynamic(b, k, n):
 
 
 @pytest.mark.parametrize("name", ["conv2", "conv4", "conv6"])
-@pytest.mark.parametrize("b", [1, 3, 150])
+@pytest.mark.parametrize("b", [1, 3, 150, 151])
 def test_conv_tc_fused_pool(qparams, qparams_np, name, b):
     """conv + aten::quantized_max_pool2d fused in the epilogue == pooling the oracle's conv output."""
     from convnet_quantization_b200 import ops
@@ -219,9 +219,10 @@ def test_conv12_fused(qparams, qparams_np, b, gain):
 
 
 @pytest.mark.parametrize("name,b,pool", [("conv3", 900, False), ("conv5", 1300, False), ("conv6", 1300, True),
-                                         ("conv4", 450, True)])
+                                         ("conv4", 450, True), ("conv2", 701, True), ("conv2", 450, False)])
 def test_conv_tc_many_bands_per_cta(qparams, qparams_np, name, b, pool):
-    """Batches large enough that every persistent CTA walks several bands: the weight ring wraps, the activation
+    """Batches large enough that every persistent CTA (conv2 + pool: every CTA PAIR of conv_halo2.cu, with an odd image
+    count so that the last pair is half empty) walks several bands: the weight ring wraps, the activation
     buffers and the TMEM slots change phase parity, the pipelined epilogue runs in steady state.  Oracle comparison on
     a random subset of images (the numpy restatement is the slow side), full-tensor comparison against the same
     kernel run on the subset alone."""
@@ -259,6 +260,8 @@ def test_alternate_instantiations_stay_bit_exact():
     dev = str(_lib.build(dev=True))  # the switches exist in the development library only (-DB200Q_DEV)
     for name, env in (("default", {}), ("dev", {"B200Q_LIB": dev}), ("ew16", {"B200Q_LIB": dev, "B200Q_HALO_EW": "16"}),
                       ("fuse12", {"B200Q_LIB": dev, "B200Q_FUSE12": "1"}), ("no_halo", {"B200Q_LIB": dev, "B200Q_NO_HALO": "1"}),
+                      ("no_cta2", {"B200Q_LIB": dev, "B200Q_NO_CTA2": "1"}), ("h2_slots4", {"B200Q_LIB": dev, "B200Q_H2_SLOTS": "4"}),
+                      ("no_small", {"B200Q_LIB": dev, "B200Q_NO_SMALL": "1"}),
                       ("ignored", {"B200Q_HALO_DEBUG": "14", "B200Q_PAIR_DEBUG": "46", "B200Q_NO_HALO": "1"})):
         e = dict(os.environ)
         e.update(env)
