@@ -435,7 +435,9 @@ int conv3x3_halo_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_c
     return 0;
   }
   if (L->img == 16 && L->cin == 64 && L->cout == 128 && !pool) {
-    *rc = B200Q_HALO_CASE(16, 64, 128, 3, false, 8);
+    // three images per band amortise the per-band hand-shakes at large batches; below three bands per SM one image per
+    // band keeps more SMs busy (batch 128: 128 CTAs instead of 43)
+    *rc = b < 3 * (int64_t)num_sms() ? B200Q_HALO_CASE(16, 64, 128, 1, false, 8) : B200Q_HALO_CASE(16, 64, 128, 3, false, 8);
     return 0;
   }
   if (L->img == 16 && L->cin == 128 && L->cout == 128) {  // weights (144 KiB) + two single-image bands

@@ -237,11 +237,11 @@ def test_engine_rejects_foreign_tensors(qparams):
             eng.forward(torch.zeros(4, 3, 32, 32, device="cuda:1"))
 
 
-@pytest.mark.parametrize("b", [18, 19, 32, 33, 37, 38, 74, 75, 148, 149])
+@pytest.mark.parametrize("b", [18, 19, 32, 33, 37, 38, 74, 75, 148, 149, 443, 444])
 def test_kernel_selection_thresholds_are_bit_exact(engine, oracle_model, b):
     """Every batch size at which b200q_conv3x3_tc / b200q_linear_tc / the forward switch kernels (small-batch N-tile-64
-    tiles <-> band-resident kernels per layer: 37|38, 74|75, 148|149; fused head <-> two-kernel head: 32|33; fc1 tile
-    shape) - logits vs the CPU oracle, eager and as a CUDA graph."""
+    tiles <-> band-resident kernels per layer: 37|38, 74|75, 148|149; one <-> three images per conv3 band: 443|444; fused
+    head <-> two-kernel head: 32|33; fc1 tile shape) - logits vs the CPU oracle, eager and as a CUDA graph."""
     from convnet_quantization_b200 import synth
     from oracle import torch_oracle as TO
     x = synth.images_f32(b, seed=900 + b)
