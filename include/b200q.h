@@ -185,9 +185,14 @@ typedef struct b200q_static_net {
   float out_scale;              /* fc2 output scale (DeQuantStub) ; zp is fc2.rq.zp_out */
 } b200q_static_net;
 
-/* Bytes of device workspace b200q_static_forward needs for batch b. */
+/* Bytes of device workspace b200q_static_forward needs for batch b (two ping-pong activation buffers of b x 64 KiB plus
+ * 2 KiB).  The contents need no initialisation; one workspace serves one forward at a time (forwards on different
+ * streams need their own). */
 int64_t b200q_static_workspace_bytes(int64_t b);
 /* fp32 NCHW [b,3,32,32] -> fp32 logits [b,10]; restates models/baseline_model.py:58-83 on the converted model.
+ * Enqueues eight kernels on `stream` (seven for b <= 32: fc1 + fc2 + dequantize fused), picking per layer the kernel
+ * shape that fits the batch (small-batch tiles, one or three images per band, CTA pairs for conv2); results do not
+ * depend on that choice.
  * taps (optional, may be NULL): 12 device pointers receiving the uint8 activations after
  * quant, conv1, conv2, pool1, conv3, conv4, pool2, conv5, conv6, pool3, fc1, fc2 (NHWC) for parity tests. */
 int b200q_static_forward(const b200q_static_net* net, const float* x, float* logits, int64_t b,
