@@ -93,6 +93,10 @@ class B200StaticQuantizedNet(_GpuResident):
     # of the LAST chunk.  2048 images = 24 MiB per copy, still far above the size where PCIe copies lose efficiency.
     HOST_CHUNK = int(os.environ.get("B200Q_HOST_CHUNK", "2048"))
     TAIL_MIN = int(os.environ.get("B200Q_TAIL_MIN", "256"))
+    # uint8 route: 3 KiB per image crosses PCIe at ~17 M images/s, the kernels run at ~7.6 M images/s, so that pipeline
+    # is COMPUTE-bound and what is exposed is the copy of the FIRST chunk.  Chunks therefore ramp up: a small first one
+    # (fast fill), each next one twice the size (its copy still finishes inside the kernels of the one before).
+    U8_FIRST_CHUNK = int(os.environ.get("B200Q_U8_FIRST_CHUNK", "1024"))
 
     def __init__(self, qparams: dict, device=None):
         super().__init__(device)
@@ -134,6 +138,15 @@ class B200StaticQuantizedNet(_GpuResident):
             lo += rest - tail
         yield lo, b - lo
 
+    def _chunks_ramp(self, b: int, first: int, cap: int):
+        """(offset, size) for the compute-bound uint8 pipeline: ``first``, 2*first, 4*first ... capped at ``cap``."""
+        lo, n = 0, max(1, first)
+        while b - lo > n:
+            yield lo, n
+            lo += n
+            n = min(2 * n, cap)
+        yield lo, b - lo
+
     def _forward_host(self, x: torch.Tensor, u8: bool = False) -> torch.Tensor:
         b = x.shape[0]
         x = x.contiguous()
@@ -150,7 +163,8 @@ class B200StaticQuantizedNet(_GpuResident):
         cur = torch.cuda.current_stream(self.engine_device)
         for s in pipe["streams"]:
             s.wait_stream(cur)
-        for i, (lo, n) in enumerate(self._chunks(b, chunk)):
+        plan = self._chunks_ramp(b, self.U8_FIRST_CHUNK, chunk) if u8 else self._chunks(b, chunk)
+        for i, (lo, n) in enumerate(plan):
             k = i & 1
             with torch.cuda.stream(pipe["streams"][k]):  # per-stream buffers: reuse is ordered by the stream itself
                 xin, yout = (pipe["xu8"] if u8 else pipe["x"])[k][:n], (pipe["yu8"] if u8 else pipe["y"])[k][:n]
