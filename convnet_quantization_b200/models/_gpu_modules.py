@@ -81,12 +81,12 @@ class _GpuResident(nn.Module):
         return y.to(x.device)  # device -> host (or peer) copy: synchronises by itself
 
 
-class B200StaticQuantizedNet(_GpuResident):
-    """True static-PTQ int8 ``SimpleConvNet`` (all eight layers int8, fbgemm-exact requantisation) on a B200.
-
-    Host inputs (what ``utils/model_evaluator.py`` hands over, and ``utils/inference_benchmark.py`` with
+class _HostPipelined(_GpuResident):
+    """Host inputs (what ``utils/model_evaluator.py`` hands over, and ``utils/inference_benchmark.py`` with
     ``device='cpu'``) are processed in chunks on two CUDA streams, so the host->device copy of chunk i+1 overlaps
-    the kernels of chunk i; logits come back through a pinned staging buffer."""
+    the kernels of chunk i; logits come back through a pinned staging buffer.  Only for nets whose result for an image
+    does not depend on the rest of the batch (the int8 static and sandwich nets; NOT the dynamic one, whose activation
+    qparams come from the whole batch).  Subclasses provide ``_chunk_forward(xin, yout, u8)``."""
 
     # images per pipelined chunk (B200Q_HOST_CHUNK overrides, for tuning).  The pipeline is bound by the host->device
     # copy (12 KiB of fp32 per image over PCIe), so what the chunk size controls is the un-overlapped tail: the kernels
@@ -98,16 +98,7 @@ class B200StaticQuantizedNet(_GpuResident):
     # (fast fill), each next one twice the size (its copy still finishes inside the kernels of the one before).
     U8_FIRST_CHUNK = int(os.environ.get("B200Q_U8_FIRST_CHUNK", "1024"))
 
-    def __init__(self, qparams: dict, device=None):
-        super().__init__(device)
-        self.qparams = qparams
-        self.engine = StaticEngine(qparams, self.engine_device)
-        self._pipe = None
-
-    def _rehome(self, device):
-        self.engine = StaticEngine(self.qparams, device)
-        self.engine_device = device
-        self._pipe = None
+    _pipe = None
 
     def _pipeline(self):
         if self._pipe is None:
@@ -169,14 +160,32 @@ class B200StaticQuantizedNet(_GpuResident):
             with torch.cuda.stream(pipe["streams"][k]):  # per-stream buffers: reuse is ordered by the stream itself
                 xin, yout = (pipe["xu8"] if u8 else pipe["x"])[k][:n], (pipe["yu8"] if u8 else pipe["y"])[k][:n]
                 xin.copy_(x[lo:lo + n], non_blocking=True)
-                if u8:
-                    self.engine.forward_u8(xin, out=yout)
-                else:
-                    self.engine.forward(xin, out=yout)
+                self._chunk_forward(xin, yout, u8)
                 out[lo:lo + n].copy_(yout, non_blocking=True)
         for s in pipe["streams"]:
             s.synchronize()
         return out.clone()  # the pinned staging buffer is reused by the next call
+
+
+class B200StaticQuantizedNet(_HostPipelined):
+    """True static-PTQ int8 ``SimpleConvNet`` (all eight layers int8, fbgemm-exact requantisation) on a B200."""
+
+    def __init__(self, qparams: dict, device=None):
+        super().__init__(device)
+        self.qparams = qparams
+        self.engine = StaticEngine(qparams, self.engine_device)
+        self._pipe = None
+
+    def _rehome(self, device):
+        self.engine = StaticEngine(self.qparams, device)
+        self.engine_device = device
+        self._pipe = None
+
+    def _chunk_forward(self, xin, yout, u8):
+        if u8:
+            self.engine.forward_u8(xin, out=yout)
+        else:
+            self.engine.forward(xin, out=yout)
 
     @torch.no_grad()
     def forward(self, x):
@@ -279,7 +288,7 @@ class B200DynamicQuantizedNet(_GpuResident):
         return sd
 
 
-class B200SandwichQuantizedNet(_GpuResident):
+class B200SandwichQuantizedNet(_HostPipelined):
     """The custom variant *as intended* (``models/custom_quantization_model.py:34-58, 202-261``):
     each conv and ``fc1`` is QuantStub -> int8 layer -> DeQuantStub, ReLU / max-pool run in fp32 between the
     sandwiches, ``fc2`` is fp32.  On the GPU the fp32 detours collapse without changing a bit:
@@ -317,6 +326,10 @@ class B200SandwichQuantizedNet(_GpuResident):
     def _rehome(self, device):
         self._build(device)
         self.engine_device = device
+        self._pipe = None
+
+    def _chunk_forward(self, xin, yout, u8):
+        yout.copy_(self._forward_dev(xin))
 
     @torch.no_grad()
     def _forward_dev(self, x, taps: dict | None = None):
@@ -342,6 +355,8 @@ class B200SandwichQuantizedNet(_GpuResident):
     def forward(self, x):
         if x.shape[0] == 0:
             return torch.empty((0, 10), dtype=torch.float32, device=x.device)
+        if not x.is_cuda and x.dim() == 4:  # per-image arithmetic: chunking changes no bit of the int8 layers
+            return self._forward_host(x.float())
         return self._run(x, self._forward_dev)
 
     @torch.no_grad()

@@ -232,6 +232,26 @@ def test_custom_sandwich_vs_reference_golden(golden, sd, fp32_net):
     assert tuple(q(xb[:0]).shape) == (0, 10)
 
 
+def test_custom_sandwich_host_pipeline_is_chunking_invariant(sd):
+    """Host input to the sandwich net goes through the chunked two-stream pipeline (several chunks + split tail).  The
+    int8 layers are per-image arithmetic, so chunking changes no bit of them; fc2 is an fp32 cuBLAS GEMM that may pick
+    another kernel (summation order) for another batch size, hence fp32-rounding tolerance on the logits."""
+    from convnet_quantization_b200 import synth
+    from convnet_quantization_b200.models.custom_quantization_model import CustomQuantizationModel
+    cm = CustomQuantizationModel(mode="sandwich")
+    cm.load_state_dict(sd)
+    q = cm.quantize()
+    x = synth.images_f32(5000, seed=13)
+    want = q(x.cuda()).cpu()
+    got = q(x)
+    tol = dict(rtol=1e-5, atol=1e-5 * float(want.abs().max()))
+    assert not got.is_cuda
+    torch.testing.assert_close(got, want, **tol)
+    assert torch.equal(got.argmax(1), want.argmax(1))
+    assert torch.equal(q(x.pin_memory()), got)  # second call: staging buffers reused, same chunking -> same bytes
+    torch.testing.assert_close(q(x[:300]), want[:300], **tol)
+
+
 def test_gpu_side_calibration(sd, fp32_net, oracle_model):
     """``StaticPTQModel.quantize(loader, calibration_device='cuda')`` runs the calibration forward and
     the observers' reductions on the GPU.  The observers are exact (test_histogram_observer_on_gpu_equals_cpu_observer);
