@@ -94,9 +94,14 @@ class _HostPipelined(_GpuResident):
     HOST_CHUNK = int(os.environ.get("B200Q_HOST_CHUNK", "2048"))
     TAIL_MIN = int(os.environ.get("B200Q_TAIL_MIN", "256"))
     # uint8 route: 3 KiB per image crosses PCIe at ~17 M images/s, the kernels run at ~7.6 M images/s, so that pipeline
-    # is COMPUTE-bound and what is exposed is the copy of the FIRST chunk.  Chunks therefore ramp up: a small first one
-    # (fast fill), each next one twice the size (its copy still finishes inside the kernels of the one before).
-    U8_FIRST_CHUNK = int(os.environ.get("B200Q_U8_FIRST_CHUNK", "1024"))
+    # is COMPUTE-bound and what is exposed is the copy of the FIRST chunk.  Chunks therefore ramp up: a smaller first one
+    # (fast fill), the next ones twice the size (their copies still finish inside the kernels of the chunk before).
+    # The cap keeps the doubling short: on a host whose links are shared by eight GPUs the copy rate per GPU falls to
+    # about the compute rate, and every doubling then stalls the kernels for one chunk.  Measured (first, cap) at
+    # N = 1 / N = 8 ranks, M images/s: (8192, 8192) 6.3-6.5 / 45.6, (1024, 8192) 7.0-7.1 / 42.1, (2048, 4096) 7.0 / 47.1
+    # (profiles/r02_e2e_timeline.txt, r02_u8_plan_n8.txt).
+    U8_FIRST_CHUNK = int(os.environ.get("B200Q_U8_FIRST_CHUNK", "2048"))
+    U8_MAX_CHUNK = int(os.environ.get("B200Q_U8_MAX_CHUNK", "4096"))
 
     _pipe = None
 
@@ -142,9 +147,7 @@ class _HostPipelined(_GpuResident):
         b = x.shape[0]
         x = x.contiguous()
         pipe = self._pipeline()
-        # uint8 pixels are a quarter of the bytes: four times the images per chunk (same 24 MiB per copy), which also
-        # keeps the kernels at an efficient batch size on a path that is compute- rather than PCIe-bound
-        chunk = 4 * self.HOST_CHUNK if u8 else self.HOST_CHUNK
+        chunk = self.U8_MAX_CHUNK if u8 else self.HOST_CHUNK
         if u8 and pipe["xu8"] is None:
             pipe["xu8"] = [torch.empty((chunk, 32, 32, 3), dtype=torch.uint8, device=self.engine_device) for _ in range(2)]
             pipe["yu8"] = [torch.empty((chunk, 10), dtype=torch.float32, device=self.engine_device) for _ in range(2)]

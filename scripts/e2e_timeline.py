@@ -57,7 +57,7 @@ def timeline(u8: bool):
     src = pix if u8 else x
     q.forward_uint8(src) if u8 else q(src)  # buffers, graphs
     pipe = q._pipeline()
-    chunk = 4 * q.HOST_CHUNK if u8 else q.HOST_CHUNK
+    chunk = q.U8_MAX_CHUNK if u8 else q.HOST_CHUNK
     plan = list(q._chunks_ramp(B, q.U8_FIRST_CHUNK, chunk) if u8 else q._chunks(B, chunk))
     out = pipe["out"][:B]
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -201,10 +201,12 @@ for name, mk in [("fp32_alt_2048_halve256", lambda: AltStreamsPipe(2048, 256)), 
     del p
 res["alternatives"] = alts
 # the module's uint8 route under other ramps
-for first in (256, 512, 2048, 4096, 8192):
-    q.U8_FIRST_CHUNK = first
-    res[f"module_uint8_first{first}"] = wall(lambda: q.forward_uint8(pix))
-q.U8_FIRST_CHUNK = 1024
+first0, cap0 = q.U8_FIRST_CHUNK, q.U8_MAX_CHUNK
+for first, cap in ((512, 4096), (1024, 2048), (1024, 4096), (1024, 8192), (2048, 2048), (2048, 4096), (4096, 4096), (8192, 8192)):
+    q.U8_FIRST_CHUNK, q.U8_MAX_CHUNK, q._pipe = first, cap, None
+    assert torch.equal(q.forward_uint8(pix), ref8)
+    res[f"module_uint8_first{first}_cap{cap}"] = wall(lambda: q.forward_uint8(pix))
+q.U8_FIRST_CHUNK, q.U8_MAX_CHUNK, q._pipe = first0, cap0, None
 print(json.dumps(res))
 for k, v in res.items():
     if isinstance(v, dict) and "median_ms" in v:
