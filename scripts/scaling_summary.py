@@ -10,7 +10,10 @@ for n in (1, 2, 4, 8):
     batch = b["config"].get("batch_per_gpu", 16384)
     bytes_per_step = b["e2e"]["h2d_bytes_per_step"]
     ceiling = n * batch / (bytes_per_step / (gbs_min * 1e9))  # timing is max over ranks: the slowest GPU's copy sets it
-    rows.append({"n_gpus": n, "value": b["value"], "e2e": b["e2e"]["value"], "e2e_u8": b["e2e_u8"]["value"],
+    u8 = b if n == 1 else json.load(open(os.path.join(P, f"r02_bench_n{n}_rerun.json")))  # final uint8 chunk plan
+    rows.append({"n_gpus": n, "value": b["value"], "e2e": b["e2e"]["value"], "e2e_u8": u8["e2e_u8"]["value"],
+                 "rerun_other_allocation": None if n == 1 else {"value": u8["value"], "e2e": u8["e2e"]["value"],
+                                                                "source": f"profiles/r02_bench_n{n}_rerun.json"},
                  "parity_bit_exact": b["parity"]["bit_exact"],
                  "h2d_aggregate_gbs_fp32_batch": h["aggregate_gbs"]["fp32_batch_192MiB"], "h2d_min_per_gpu_gbs": gbs_min,
                  "h2d_min_per_gpu_gbs_uint8_batch": h["min_per_gpu_gbs"]["uint8_batch_48MiB"],
