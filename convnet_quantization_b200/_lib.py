@@ -20,7 +20,7 @@ LIB_PATH = PKG_DIR / "libb200q.so"
 # switches that disable kernel roles / select alternate instantiations for timing.  Only tests and A-B scripts load it.
 DEV_LIB_PATH = PKG_DIR / "libb200q_dev.so"
 BUILD_DIR = PKG_DIR / "build"
-SOURCES = ("runtime.cu", "elementwise.cu", "simt.cu", "igemm_tc.cu", "conv_halo.cu", "conv_halo2.cu", "conv_pair.cu", "conv1_tc.cu",
+SOURCES = ("runtime.cu", "elementwise.cu", "simt.cu", "igemm_tc.cu", "conv_halo.cu", "conv_halo2.cu", "conv_pair.cu", "conv_small.cu", "conv1_tc.cu",
            "linear_dynamic_tc.cu", "net.cu")
 DEV_SOURCES = SOURCES + ("conv12_fused.cu",)
 # -fmad=false: the requantisation is specified as separately rounded fp32 add / mul; ptxas was

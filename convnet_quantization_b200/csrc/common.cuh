@@ -41,6 +41,9 @@ int conv3x3_halo2_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_
 // it zero); returns 1 when the shapes / batch are not covered
 int fc_head_small_dispatch(const uint8_t* x, uint8_t* h, float* logits, unsigned int* ticket, int64_t b,
                            const b200q_linear* fc1, const b200q_linear* fc2, float out_scale, cudaStream_t s, int* rc);
+// conv_small.cu: CUDA-core kernel for a handful of images (one round trip per layer); returns 1 when not covered
+int conv3x3_tiny_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, bool pool, cudaStream_t s,
+                          int* rc);
 // conv_pair.cu: pair-interleaved halo kernel for the 8x8 layers (conv5, conv6); returns 1 when not covered
 int conv3x3_pair_dispatch(const uint8_t* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, bool pool, cudaStream_t s,
                           int* rc);
@@ -77,6 +80,13 @@ int launch_kernel(const char* what, void (*kernel)(KArgs...), int grid, int bloc
 // layer kernel is data-dependent on its loader's reads).  Both are no-ops in a launch without the PDL attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// uint8x4 . int8x4 + c
+__device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+  return d;
+}
 
 // ---------------------------------------------------------------- exact fbgemm requantisation
 // t = f32(acc) + bdiv; t = t * mult; q = clamp(rne(t) + zp, lo, 255).  Intrinsics forbid FMA contraction

@@ -427,6 +427,21 @@ static bool small_batch_off() {
   return v == 1;
 }
 
+// Largest batch that takes the CUDA-core kernel of conv_small.cu.  -DB200Q_DEV builds only: B200Q_TINY_MAX_B overrides
+// it (0 disables the kernel; A-B timing only).
+constexpr int CONV_TINY_MAX_B = 2;
+static int tiny_max_b() {
+#ifndef B200Q_DEV
+  return CONV_TINY_MAX_B;
+#endif
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200Q_TINY_MAX_B");
+    v = e ? atoi(e) : CONV_TINY_MAX_B;
+  }
+  return v;
+}
+
 // -DB200Q_DEV builds only: B200Q_NO_HALO=1 routes the cin=64 layers through the shifted-TMA kernel as well (A-B testing only).
 static bool no_halo() {
 #ifndef B200Q_DEV
@@ -450,6 +465,11 @@ extern "C" int b200q_conv3x3_tc(const uint8_t* x, uint8_t* y, int64_t b, const b
   cudaStream_t s = (cudaStream_t)stream;
   const bool streamed = force_streamed();
   const bool pool = pool2x2 != 0;
+  // A handful of images: one round trip per layer on the CUDA cores (conv_small.cu).
+  if (b <= tiny_max_b()) {
+    int rc = 0;
+    if (conv3x3_tiny_dispatch(x, y, b, L, pool, s, &rc) == 0) return rc;
+  }
   // Small batches (the latency-bound regime the whole-network executor serves): the band-resident kernels below give a
   // whole image (or four) to ONE CTA, so at batch 1 a layer is a serial walk over its tiles on one SM.  When the layer
   // cut into 128-pixel x 64-channel tiles still fits in about two waves of CTAs, it runs as that many independent CTAs

@@ -5,22 +5,20 @@
 
 namespace b200q {
 
-__device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c) {
-  int d;
-  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
-  return d;
-}
-
 // =========================================================================================================
 // First conv (cin = 3 stored as 4, cout = 64, 32x32 images), optionally fused with aten::quantize_per_tensor.
 // Block = 8 output rows x 32 columns of one image (256 threads, one pixel each, all 64 output channels).
 // The quantized halo (10 x 34 pixels, one 32-bit word per pixel) lives in shared memory; out-of-image taps hold
 // zp_x (real-domain zero), so acc_true = sum_all x*w - zp_x*sum_all w = raw - corr[interior][c] for every pixel.
 // Weights [9 taps][64 cout] words are read as broadcast uint4 (4 output channels per LDS.128).
+// CGROUPS: 16-channel groups per CTA.  4 = all 64 channels (grid.y = 1); 1 = one group per CTA (grid.y = 4), the shape
+// the whole-network executor uses up to CONV1_TINY_MAX_B images (16 CTAs per image, ~350 instructions per thread: the
+// tensor-core kernel of conv1_tc.cu spends ~6 us on a few images in barrier / TMEM / MMA round trips).
 constexpr int C1_ROWS = 8;
 constexpr int C1_COUT = 64;
+constexpr int CONV1_TINY_MAX_B = 32;  // measured: ahead of conv1_tc.cu up to 32 images, level at 64 (r02 sweep)
 
-template <bool FUSED_QUANT>
+template <bool FUSED_QUANT, int CGROUPS>
 __global__ void __launch_bounds__(256) conv1_kernel(const void* __restrict__ xin, uint8_t* __restrict__ y,
                                                     const uint32_t* __restrict__ w_words,  // [64][9] words
                                                     const int32_t* __restrict__ corr,      // [9][64], row 4 = interior
@@ -36,6 +34,7 @@ __global__ void __launch_bounds__(256) conv1_kernel(const void* __restrict__ xin
   const int row0 = (blockIdx.x % tiles_per_img) * C1_ROWS;
   const int tid = threadIdx.x;
   const uint32_t zp_word = (uint32_t)zp_x * 0x01010101u;
+  pdl_launch_dependents();
 
   for (int i = tid; i < 9 * C1_COUT; i += 256) {
     // s_w[tap][c/4].{x,y,z,w} = word(tap, c)
@@ -47,6 +46,7 @@ __global__ void __launch_bounds__(256) conv1_kernel(const void* __restrict__ xin
     s_bdiv[tid] = __ldg(bdiv + tid);
     s_corr[tid] = __ldg(corr + 4 * C1_COUT + tid);
   }
+  pdl_wait();  // y may still be read by the previous kernel of the stream (weights and constants above are not its output)
   for (int i = tid; i < (C1_ROWS + 2) * 34; i += 256) {
     const int r = i / 34 + row0 - 1, c = i % 34 - 1;
     uint32_t word = zp_word;
@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(256) conv1_kernel(const void* __restrict__ xin
   const int lo = relu ? zp_out : 0;
   uint8_t* out = y + ((image * img + row0 + lr) * img + lc) * (int64_t)C1_COUT;
 #pragma unroll
-  for (int cg = 0; cg < C1_COUT / 16; ++cg) {
+  for (int cgi = 0; cgi < CGROUPS; ++cgi) {
+    const int cg = blockIdx.y * CGROUPS + cgi;
     uint32_t packed[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -400,6 +401,19 @@ static int check_conv(const void* x, const void* y, int64_t b, const b200q_conv3
   return 0;
 }
 
+// -DB200Q_DEV builds only: B200Q_CONV1_TINY_MAX_B overrides the cut-off (0 disables the shape; A-B timing only).
+static int conv1_tiny_max_b() {
+#ifndef B200Q_DEV
+  return CONV1_TINY_MAX_B;
+#endif
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200Q_CONV1_TINY_MAX_B");
+    v = e ? atoi(e) : CONV1_TINY_MAX_B;
+  }
+  return v;
+}
+
 static int conv_first_impl(const void* x, uint8_t* y, int64_t b, const b200q_conv3x3* L, bool fused, float inv_scale,
                            void* stream) {
   int rc = check_conv(x, y, b, L);
@@ -409,6 +423,27 @@ static int conv_first_impl(const void* x, uint8_t* y, int64_t b, const b200q_con
                 L->img);
   B200Q_REQUIRE((uintptr_t)y % 16 == 0 && (uintptr_t)x % 4 == 0, "conv3x3_first: misaligned buffers");
   if (b == 0) return 0;
+  if (fused && b <= conv1_tiny_max_b()) {  // a few images: 16 CUDA-core CTAs per image, one round trip
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(b * (L->img / C1_ROWS)), 4);
+    cfg.blockDim = dim3(256);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    if (pdl_enabled()) {
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+    }
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, conv1_kernel<true, 1>, x, y, reinterpret_cast<const uint32_t*>(L->w),
+                                             L->corr, L->rq.mult, L->rq.bdiv, (int)L->zp_x, (int)L->rq.zp_out,
+                                             (int)L->rq.relu, inv_scale, (int)L->img);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      return check_cuda(e, "conv1_kernel");
+    }
+    return launched("conv1_kernel");
+  }
   if (fused) {  // tensor-core version unless the layer lacks host mirrors / the BOUNDED flag (dev builds: or B200Q_NO_CONV1_TC=1)
 #ifdef B200Q_DEV
     static int no_tc = -1;
@@ -426,11 +461,11 @@ static int conv_first_impl(const void* x, uint8_t* y, int64_t b, const b200q_con
   const unsigned grid = (unsigned)(b * (L->img / C1_ROWS));
   const uint32_t* ww = reinterpret_cast<const uint32_t*>(L->w);
   if (fused)
-    conv1_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, ww, L->corr, L->rq.mult, L->rq.bdiv, L->zp_x,
-                                                               L->rq.zp_out, L->rq.relu, inv_scale, L->img);
+    conv1_kernel<true, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, ww, L->corr, L->rq.mult, L->rq.bdiv, L->zp_x,
+                                                                  L->rq.zp_out, L->rq.relu, inv_scale, L->img);
   else
-    conv1_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, ww, L->corr, L->rq.mult, L->rq.bdiv, L->zp_x,
-                                                                L->rq.zp_out, L->rq.relu, 0.f, L->img);
+    conv1_kernel<false, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, ww, L->corr, L->rq.mult, L->rq.bdiv, L->zp_x,
+                                                                   L->rq.zp_out, L->rq.relu, 0.f, L->img);
   return launched("conv1_kernel");
 }
 

@@ -28,7 +28,7 @@ def _rand_u8(shape, seed):
     return torch.randint(0, 256, shape, dtype=torch.uint8, generator=torch.Generator().manual_seed(seed))
 
 
-@pytest.mark.parametrize("b", [1, 5])
+@pytest.mark.parametrize("b", [1, 5, 40])  # <= 32 images: CUDA-core shape (16 CTAs per image); above: conv1_tc.cu
 def test_conv1_first_and_fused(qparams, qparams_np, b):
     from convnet_quantization_b200 import ops, synth
     from oracle import int_ops as IO
@@ -125,6 +125,30 @@ def test_linear_dynamic(b, k, n):
         assert torch.equal(got, want)  # bit-exact (fbgemm's fma forms), far inside the 1e-3 the north star asks for
 
 
+@pytest.mark.parametrize("name", ["conv2", "conv3", "conv4", "conv5", "conv6"])
+@pytest.mark.parametrize("pool", [False, True])
+@pytest.mark.parametrize("b", [1, 2])
+def test_conv_tiny_batches(qparams, qparams_np, name, pool, b):
+    """One or two images take the CUDA-core kernel (csrc/conv_small.cu: K split across the lanes, zero-point halo in
+    shared memory, exact requantisation, pooling on the requantised bytes): bit-exact against the integer oracle and
+    identical to what the tensor-core kernels give for the same images inside a larger batch."""
+    from convnet_quantization_b200 import ops
+    from oracle import int_ops as IO
+    pc, s, zp = _packed(qparams, name)
+    x = _rand_u8((b, pc.img, pc.img, pc.cin), 31 * b + len(name))
+    x[0, :2] = 255  # saturating rows at the top border
+    x[-1, -1] = 0
+    want = _want_conv(x.numpy(), s, zp, qparams_np[name])
+    if pool:
+        want = IO.max_pool2x2(want)
+    got = ops.conv2d_q(x.cuda(), pc, pool2x2=pool, impl="tc")
+    torch.cuda.synchronize()
+    bad = got.cpu().numpy() != want
+    assert not bad.any(), f"{name} b={b} pool={pool}: {int(bad.sum())} / {bad.size} mismatches; first at {np.argwhere(bad)[:5].tolist()}"
+    big = torch.cat([x, _rand_u8((5, pc.img, pc.img, pc.cin), 3)]).cuda()  # 6-7 images: small-batch tensor-core shape
+    assert torch.equal(ops.conv2d_q(big, pc, pool2x2=pool, impl="tc")[:b], got)
+
+
 @pytest.mark.parametrize("name", ["conv2", "conv4", "conv6"])
 @pytest.mark.parametrize("b", [1, 3, 150, 151])
 def test_conv_tc_fused_pool(qparams, qparams_np, name, b):
@@ -155,11 +179,12 @@ def _stress_layer(name, qparams, huge):
 @pytest.mark.parametrize("name", ["conv2", "conv3", "conv6"])
 @pytest.mark.parametrize("mode", ["huge_acc", "big_mult"])
 @pytest.mark.parametrize("pool", [False, True])
-@pytest.mark.parametrize("b", [2, 160])
+@pytest.mark.parametrize("b", [2, 3, 160])  # 2: CUDA-core kernel of conv_small.cu; 3: small-batch tensor-core shape
 def test_conv_tc_requant_fallback_paths(qparams, name, mode, pool, b):
     """The conversion-free epilogue must hand over to the exact I2F/F2I form (run-time range test, or the BOUNDED flag
-    withheld at pack time) and stay bit-exact: accumulators up to ~7e7 and multipliers > 0.5.  b = 2 runs the small-batch
-    kernel (shifted TMA, N tile 64), b = 160 the band-resident kernels (conv_halo.cu / conv_pair.cu)."""
+    withheld at pack time) and stay bit-exact: accumulators up to ~7e7 and multipliers > 0.5.  b = 3 runs the small-batch
+    kernel (shifted TMA, N tile 64), b = 160 the band-resident kernels (conv_halo.cu / conv_pair.cu); b = 2 the CUDA-core
+    kernel (conv_small.cu), which always requantises with the exact form."""
     from convnet_quantization_b200 import _lib, ops
     from convnet_quantization_b200.packing import PackedConv
     from tests.conftest import qparams_to_numpy
@@ -273,7 +298,7 @@ def test_alternate_instantiations_stay_bit_exact():
 
 @pytest.mark.parametrize("name,pool", [("conv2", False), ("conv2", True), ("conv3", False), ("conv4", False), ("conv4", True),
                                        ("conv5", False), ("conv6", False), ("conv6", True)])
-@pytest.mark.parametrize("b", [2, 37])
+@pytest.mark.parametrize("b", [3, 37])
 def test_conv_tc_without_host_mirrors(qparams, qparams_np, name, pool, b):
     """Documented ABI branch (include/b200q.h, b200q_requant.mult_host): with corr_host / mult_host / bdiv_host NULL the
     kernels that take their constants as kernel parameters are not eligible and b200q_conv3x3_tc must run the

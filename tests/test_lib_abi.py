@@ -42,7 +42,7 @@ def test_dev_library_is_a_superset_and_product_has_no_dev_code():
     assert dev.b200q_abi_version() == 4
     product = open(_lib.LIB_PATH, "rb").read()
     for switch in (b"B200Q_HALO_DEBUG", b"B200Q_PAIR_DEBUG", b"B200Q_NO_HALO", b"B200Q_TC_STREAM_WEIGHTS", b"B200Q_FUSE12",
-                   b"B200Q_HALO_EW", b"B200Q_NO_CONV1_TC", b"B200Q_NO_CTA2", b"B200Q_H2_SLOTS", b"B200Q_NO_SMALL",
+                   b"B200Q_HALO_EW", b"B200Q_NO_CONV1_TC", b"B200Q_NO_CTA2", b"B200Q_H2_SLOTS", b"B200Q_NO_SMALL", b"B200Q_TINY_MAX_B", b"B200Q_CONV1_TINY_MAX_B",
                    b"B200Q_EAGER_PDL", b"conv12_fused"):
         assert switch not in product, f"{switch.decode()} must not be compiled into the product library"
     assert b"B200Q_HALO_DEBUG" in open(_lib.DEV_LIB_PATH, "rb").read()
