@@ -20,6 +20,15 @@ TAP_SHAPES = {  # per image, NHWC (quant is NHWC4: channel 3 is padding)
 
 _NULL_CTX = contextlib.nullcontext()
 
+# The current stream's raw handle without building a torch.cuda.Stream object (1.5 us -> 0.2 us on the batch-1 path).
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+def _current_stream_handle(device_index: int) -> int:
+    if _raw_stream is not None:
+        return _raw_stream(device_index)
+    return torch.cuda.current_stream(device_index).cuda_stream
+
 
 class _Graph:
     """One captured forward (``b200q_graph_*``): fixed batch, fixed input / logits buffers, private workspace."""
@@ -161,7 +170,7 @@ class StaticEngine:
                 if g is None and graph:  # forced: capture right away
                     g = self._graph_for(x, out)
                 if g is not None:
-                    g.launch(torch.cuda.current_stream().cuda_stream)
+                    g.launch(_current_stream_handle(self.device.index))
                     return out if out is not None else g.logits.clone()
             logits = out if out is not None else torch.empty((b, 10), dtype=torch.float32, device=self.device)
             ws = self._workspace(b)

@@ -192,7 +192,13 @@ class B200StaticQuantizedNet(_HostPipelined):
 
     @torch.no_grad()
     def forward(self, x):
-        if not x.is_cuda and x.dim() == 4 and x.shape[0] > 0:
+        if x.is_cuda:
+            if x.dtype is torch.float32 and x.device == self.engine_device:  # the driver's loop: no conversions to make
+                y = self.engine.forward(x)
+                if self.sync_on_forward:
+                    torch.cuda.current_stream(self.engine_device).synchronize()
+                return y
+        elif x.dim() == 4 and x.shape[0] > 0:
             return self._forward_host(x.float())
         return self._run(x, self.engine.forward)
 
