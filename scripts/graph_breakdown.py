@@ -17,7 +17,7 @@ lib = engine.lib
 names = ["quant_conv1", "conv2_pool", "conv3", "conv4_pool", "conv5", "conv6_pool", "head (fc1+fc2+dequant)"]
 side = torch.cuda.Stream(dev)
 rows = []
-for b in (1, 8, 32):
+for b in tuple(int(v) for v in os.environ.get("BREAKDOWN_BATCHES", "1,8,32").split(",")):
     x = synth.images_f32(b, seed=b).cuda()
     out = torch.empty((b, 10), device=dev)
     ws = torch.empty(int(lib.b200q_static_workspace_bytes(b)), dtype=torch.uint8, device=dev)
